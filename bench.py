@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the MPS Born machine hot path on B200.
+
+Metric (BASELINE.json): sample·site updates / s during the two-site sweep at Dmax=256.
+One "step" = one two-site step of the sweep over ALL training samples at a mid-chain bond with full bond
+dimension: merge, psi_n, S = sum psi'_n/psi_n, (all-reduce), update + renormalise, SVD split, write-back,
+one-site environment advance  (learning_step_cached + sequential_update, TNutils.py:1510-1568, :504-526).
+One sample·site update = one sample's share of one step.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (numpy oracle port)
+
+Workload "c3" (default): synthetic binarised 28x28, 60 000 samples in total (sharded over the N GPUs:
+strong scaling), L=784, D=256 everywhere (random right/left-canonical MPS, centre at the first timed bond).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N_total, L, D, first bond)
+    'c3': (60000, 784, 256, 384),
+    'c2': (1000, 784, 100, 384),
+    'c5': (10000, 784, 128, 384),
+    'tiny': (512, 64, 32, 24),
+}
+FP64_PEAK_TFLOPS = 35.7   # measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_probe_fp64_svd.jsonl)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index=0):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.gpu), '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(',')]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out['sm_mhz'] = float(np.median(sm)); out['sm_max_mhz'] = float(np.max(mx)); out['reasons'] = sorted(reasons)
+            out['samples'] = len(sm)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: numpy float64 oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(N, D, steps, seed=5):
+    """Time `steps` two-site steps (TNutils.py:1510-1568 arithmetic + sequential_update) of the oracle port
+    at bond dimension D on N samples with all host BLAS threads.  Environments are synthetic random vectors
+    (the arithmetic and its cost do not depend on their values); pixel statistics are those of the workload."""
+    from oracle import born_oracle as o
+    rng = np.random.default_rng(seed)
+    imgs = o.synthetic_images(N, 4)           # 4 sites are enough: columns 1,2 play bonds k,k+1
+    phys = o.embed(imgs)
+    # 4-site MPS with open bonds D in the middle: sites 1,2 are the pair being optimised
+    mps3 = [rng.standard_normal((1, D, 2)) / math.sqrt(2 * D), rng.standard_normal((D, D, 2)) / math.sqrt(2 * D),
+            rng.standard_normal((D, D, 2)) / math.sqrt(2 * D), rng.standard_normal((D, 1, 2)) / math.sqrt(2 * D)]
+    mps = o.from_site3(mps3)
+    lv = rng.standard_normal((N, D)); rv = rng.standard_normal((N, D))
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = o.two_site_step(mps, 1, lv, rv, phys[:, 1], phys[:, 2], 1e-3, True, 'l2', max_bond=D)
+        o.write_back(mps, 1, out['left'], out['right'])
+        new = o._grouped_apply_right(lv, o.site3(mps, 1), phys[:, 1])      # sequential_update for all N
+        new, _ = o._rescale(new, 'maxabs')
+        times.append(time.perf_counter() - t0)
+        lv = rng.standard_normal((N, D))                                   # fresh inputs (no cache reuse)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    N, L, D, k0 = WORKLOADS[args.workload]
+    cores = os.cpu_count()
+    cpu_reference_steps(min(N, 2000), D, 1)                       # warm BLAS
+    t = []
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_steps(N, D, 1)
+    t = cpu_reference_steps(N, D, args.steps)
+    ms = 1e3 * float(np.mean(t))
+    value = N / float(np.mean(t))
+    line = {
+        'impl': 'reference', 'metric': 'sample_site_updates_per_s_two_site_sweep', 'value': value,
+        'unit': 'sample·site updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': workload_config(args.workload, 1),
+        'cpu_baseline': {'value': value, 'unit': 'sample·site updates/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{args.steps} mid-chain two-site steps (psi+grad+SVD+env advance) at N={N}, D={D}, '
+                                   f'numpy float64 oracle port, BLAS threads = all {cores} host cores'},
+        'e2e': {'value': value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, world):
+    N, L, D, k0 = WORKLOADS[name]
+    return {'workload': f'{name}: synthetic binarized 28x28 (L={L}), {N} samples total, Dmax={D}, '
+                        f'mid-chain two-site steps from bond {k0} (full bond dimension), l2 renorm, cutoff 1e-10',
+            'n_samples': N, 'sites': L, 'Dmax': D, 'parallelism': f'samples sharded over {world} GPU(s), '
+            'one all-reduce of the 2 MiB gradient per step, replicated SVD' if world > 1 else 'single GPU',
+            'l2': 'each step reads fresh environment slots (R slot untouched since set-up); per-step inputs '
+                  '> L2 at N=1, L2 flushed between timed steps otherwise'}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mps_born_machines_b200 import BornEngine
+    from mps_born_machines_b200 import mpslib
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+    N, L, D, k0 = WORKLOADS[args.workload]
+    if args.samples:
+        N = args.samples
+    steps, warm = args.steps, args.warmup
+    assert k0 + warm + 2 * steps + 8 < L - 2, 'not enough sites for the requested number of steps'
+
+    # ---- set-up (untimed): data shard, MPS with the centre at the first bond, environments
+    t_setup = time.time()
+    imgs = mpslib.synthetic_images(N, L)
+    per = (N + world - 1) // world
+    shard = imgs[rank * per:min(N, (rank + 1) * per)]
+    start = k0 - warm
+    mps = mpslib.random_mps(L, D, rng=np.random.default_rng(11), centre=start)
+    eng = BornEngine(L, D, device=local, svd=args.svd)
+    eng.set_data(shard, n_total=N)
+    eng.set_mps(mps)
+    eng.env_build(start)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+    flush = None
+    if shard.shape[0] * D * 8 * 2 < 2 * 126e6:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f'cuda:{local}')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kw = dict(renorm='l2', max_bond=D, cutoff=1e-10)
+    k = start
+    for _ in range(warm):
+        eng.step(k, 1e-3, True, **kw); k += 1
+
+    # ---- timed: EXACTLY `steps` steps, device-resident inputs
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    chis = []
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+            barrier()
+        ev[i][0].record()
+        out = eng.step(k, 1e-3, True, **kw); k += 1
+        ev[i][1].record()
+        chis.append(out['chi'])
+    barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = eng.launch_count() - l0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=f'cuda:{local}')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else {}
+    value = N * steps / (dev_ms * 1e-3)
+
+    # ---- e2e: the reference-style call with HOST (pinned) site tensors in and out, every step
+    host = {}
+    def pinned(a):
+        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return tt.numpy()
+    for j in range(k, k + steps + 1):
+        host[j] = pinned(eng.get_site(j))
+    h2d = d2h = 0
+    barrier()
+    e0 = time.perf_counter()
+    for i in range(steps):
+        a, b = host[k], host[k + 1]
+        h2d += a.nbytes + b.nbytes
+        na, nb, out = eng.learning_step_host(k, a, b, 1e-3, True, **kw)
+        d2h += na.nbytes + nb.nbytes + 64
+        host[k + 1] = nb
+        k += 1
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f'cuda:{local}')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = N * steps / float(t.item())
+
+    # ---- per-kernel pass for the roofline (separate, events around each hot launch)
+    eng.set_timing(True)
+    for _ in range(max(3, min(steps, 8))):
+        eng.step(k, 1e-3, True, **kw); k += 1
+    tim = eng.get_timing()
+    eng.set_timing(False)
+    n_loc = shard.shape[0]
+    ker = {}
+    for name, flops in (('grad', 2.0 * D * D * n_loc), ('psi', 2.0 * D * D * n_loc), ('env_advance', 2.0 * D * D * n_loc)):
+        ms, cnt = tim[name]
+        if cnt:
+            ker[name] = {'ms': ms / cnt, 'tflops': flops / (ms / cnt * 1e-3) / 1e12}
+    for name in ('grad_reduce', 'merge', 'svd'):
+        ms, cnt = tim[name]
+        if cnt:
+            ker[name] = {'ms': ms / cnt}
+    dom = max(('grad', 'psi', 'env_advance'), key=lambda n: ker.get(n, {'ms': 0})['ms'])
+    peaks, peak_src = load_peaks()
+    roofline = {'bound': 'tensor', 'kernel': 'k_' + dom, 'achieved': ker[dom]['tflops'], 'peak': FP64_PEAK_TFLOPS,
+                'unit': 'TFLOP/s', 'frac': ker[dom]['tflops'] / FP64_PEAK_TFLOPS, 'traffic': None,
+                'peak_source': 'FP64: cuBLAS DGEMM 8192^3 sustained measured by tools/probe on this pool (FP64 is not in '
+                               'MEASURED_PEAKS.json; tcgen05 has no FP64 kind, DMMA.8x8x4 issue peak measured 37.1); '
+                               f'MEASURED_PEAKS.json {peak_src}',
+                'algorithmic_flops_per_launch': 2.0 * D * D * n_loc, 'kernels': ker}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cs = max(2, min(8, int(20.0 / max(0.05, 1.5e-5 * N * D / 256))))
+            tcpu = cpu_reference_steps(N, D, cs)
+            cpu = {'value': N / float(np.mean(tcpu)), 'unit': 'sample·site updates/s', 'cores': os.cpu_count(), 'kind': 'port',
+                   'sample': f'{cs} mid-chain two-site steps at N={N}, D={D} (numpy float64 oracle port, all host cores)'}
+        line = {
+            'metric': 'sample_site_updates_per_s_two_site_sweep', 'value': value, 'unit': 'sample·site updates/s',
+            'n_gpus': world, 'steps': steps, 'warmup': warm, 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args.workload, world),
+            'e2e': {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps,
+                    'd2h_bytes_per_step': d2h // steps},
+            'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clk,
+            'svd': args.svd, 'chi': int(chis[-1]), 'wall_s_timed': wall, 'setup_s': t_setup,
+            'sweep_s_extrapolated': dev_ms / steps * 1e-3 * 2 * (L - 1),
+        }
+        if cpu:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--samples', type=int, default=0)
+    ap.add_argument('--svd', default='gesvdj')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,866 @@
+// bm.cu — context + C-ABI of libbm.so (see include/bm.h).  sm_100a only; no CPU fallback anywhere.
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bm.h"
+#include "bm_kernels.cuh"
+
+using namespace bm;
+
+namespace {
+
+inline int even(int x) { return (x + 1) & ~1; }
+
+struct Chain {            // ping-pong state for left chains (logpsi, sampler)
+  int n = 0;
+  double* V[2] = {nullptr, nullptr};
+  int* e[2] = {nullptr, nullptr};
+  int* cume[2] = {nullptr, nullptr};
+  double* norm[2] = {nullptr, nullptr};
+  uint8_t* phys = nullptr;   // [L][n]
+  int* perm = nullptr;       // [n]
+  int* goff = nullptr;       // [d+1]
+  double* U = nullptr;       // uniforms
+  size_t Ucap = 0;
+  double* lnabs = nullptr; double* sign = nullptr;
+};
+
+}  // namespace
+
+struct bm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int L = 0, d = 2, Dcap = 0, ldcap = 0;
+  std::string err;
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  gesvdjInfo_t gesvdj = nullptr;
+  int svd_method = BM_SVD_GESVDJ;
+  long long launches = 0;
+
+  // site tensors, two storage forms each (see k_factor_out)
+  double* Lform = nullptr; double* Rform = nullptr; size_t site_stride = 0;
+  std::vector<int> sDl, sDr;
+
+  // training data
+  int N = 0;
+  uint8_t* phys = nullptr;     // [L][N]
+  int* perm = nullptr;         // [L-1][N] pair-grouped sample ids
+  int* goff = nullptr;         // [L-1][d*d+1]
+  std::vector<int> h_goff;
+  int* bperm = nullptr; int* bgoff = nullptr; int* bmask = nullptr;   // minibatch grouping
+  std::vector<int> h_bgoff;
+
+  // environment stack
+  double* E = nullptr; int* emax = nullptr; int* cume = nullptr; size_t slot_stride = 0;
+  int vl = 0, vr = 0;          // left environments valid for bonds 0..vl, right ones for bonds vr..L
+
+  // step workspaces
+  double *Aint = nullptr, *A2 = nullptr, *W = nullptr, *Ssv = nullptr, *U = nullptr, *V = nullptr, *G = nullptr, *sgn = nullptr;
+  double* work = nullptr; size_t lwork = 0;
+  int* info = nullptr; int* iscal = nullptr;
+  double *psi = nullptr, *winv = nullptr, *lnpsi = nullptr;
+  double* ws = nullptr; int ws_slots = 0;
+  double *partZ = nullptr, *part2 = nullptr, *scal = nullptr;
+  double* h_scal = nullptr; int* h_iscal = nullptr;   // pinned
+  double* stage = nullptr; size_t stage_cap = 0;      // device staging for host<->device tensor moves
+  int last_k = -1; int last_B = 0; const int* last_ids = nullptr;
+  int last_kchunk = 0;
+
+  Chain chain;
+
+  // optional per-kernel timing (bm_set_timing): CUDA events on the launch stream around each hot kernel
+  int timing = 0;
+  cudaEvent_t tev[2] = {nullptr, nullptr};
+  double t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // 0 advance, 1 psi, 2 grad, 3 grad_reduce, 4 merge, 5 svd, 6 update-small, 7 sample
+  long long t_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  double* slot(int j) const { return E + (size_t)j * slot_stride; }
+  int* emax_slot(int j) const { return emax + (size_t)j * N; }
+  int* cume_slot(int j) const { return cume + (size_t)j * N; }
+  double* Lf(int k) const { return Lform + (size_t)k * site_stride; }
+  double* Rf(int k) const { return Rform + (size_t)k * site_stride; }
+};
+
+namespace {
+
+int fail(bm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(c, e_ == cudaErrorMemoryAllocation ? BM_ENOMEM : BM_ECUDA,                       \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+  } while (0)
+#define LIB(call)                                                                                  \
+  do {                                                                                             \
+    int e_ = (int)(call);                                                                          \
+    if (e_ != 0) return fail(c, BM_ECUSOLVER, std::string(#call) + " failed with status " + std::to_string(e_)); \
+  } while (0)
+#define REQUIRE(cond, msg)                                                                         \
+  do {                                                                                             \
+    if (!(cond)) return fail(c, BM_EINVAL, msg);                                                   \
+  } while (0)
+#define KCHECK()                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = cudaPeekAtLastError();                                                        \
+    if (e_ != cudaSuccess) return fail(c, BM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct Timer {   // RAII: records the device time of the enclosed launches into slot `id` when timing is on
+  bm_ctx* c; int id;
+  Timer(bm_ctx* c_, int id_) : c(c_), id(id_) { if (c->timing) cudaEventRecord(c->tev[0], c->stream); }
+  ~Timer() {
+    if (!c->timing) return;
+    cudaEventRecord(c->tev[1], c->stream);
+    cudaEventSynchronize(c->tev[1]);
+    float ms = 0; cudaEventElapsedTime(&ms, c->tev[0], c->tev[1]);
+    c->t_ms[id] += ms; c->t_n[id]++;
+  }
+};
+
+template <typename T> int dalloc(bm_ctx* c, T** p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) return BM_OK;
+  CU(cudaMalloc((void**)p, count * sizeof(T)));
+  return BM_OK;
+}
+#define DALLOC(p, count)                                   \
+  do {                                                     \
+    int r_ = dalloc(c, &(p), (size_t)(count));             \
+    if (r_ != BM_OK) return r_;                            \
+  } while (0)
+
+int ensure_stage(bm_ctx* c, size_t count) {
+  if (count > c->stage_cap) {
+    DALLOC(c->stage, count);
+    c->stage_cap = count;
+  }
+  return BM_OK;
+}
+
+inline int pick_tm(int n) {
+  if (n >= 148 * 2 * 64) return 64;
+  if (n >= 148 * 32) return 32;
+  return 16;
+}
+inline int max_tiles(int n, int tm, int ngroups) { return (n + tm - 1) / tm + ngroups; }
+
+template <int TM> constexpr size_t panel_smem() { return sizeof(PanelSmem<TM>); }
+
+int set_func_attrs(bm_ctx* c) {
+  CU(cudaFuncSetAttribute(k_env_advance<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<16>()));
+  CU(cudaFuncSetAttribute(k_env_advance<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<32>()));
+  CU(cudaFuncSetAttribute(k_env_advance<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<64>()));
+  CU(cudaFuncSetAttribute(k_psi<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<16>()));
+  CU(cudaFuncSetAttribute(k_psi<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<32>()));
+  CU(cudaFuncSetAttribute(k_psi<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<64>()));
+  CU(cudaFuncSetAttribute(k_sample_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<16>()));
+  CU(cudaFuncSetAttribute(k_sample_step<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<32>()));
+  CU(cudaFuncSetAttribute(k_sample_step<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<64>()));
+  CU(cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradSmem)));
+  return BM_OK;
+}
+
+// ---- launch helpers -------------------------------------------------------------------------------
+int launch_advance(bm_ctx* c, const AdvParams& P, int nrows) {
+  Timer t_(c, 0);
+  int tm = pick_tm(nrows);
+  int grid = max_tiles(nrows, tm, P.gs.ngroups);
+  if (tm == 64) k_env_advance<64><<<grid, NTHREADS, panel_smem<64>(), c->stream>>>(P);
+  else if (tm == 32) k_env_advance<32><<<grid, NTHREADS, panel_smem<32>(), c->stream>>>(P);
+  else k_env_advance<16><<<grid, NTHREADS, panel_smem<16>(), c->stream>>>(P);
+  c->launches++;
+  KCHECK();
+  return BM_OK;
+}
+
+// site j applied to the left environment of bond j -> left environment of bond j+1 (training data)
+int adv_right(bm_ctx* c, int j) {
+  const int d = c->d, G = d * d;
+  AdvParams P{};
+  P.Ein = c->slot(j); P.ldin = c->ldcap; P.Din = c->sDl[j];
+  P.Eout = c->slot(j + 1); P.ldout = c->ldcap; P.Dout = c->sDr[j];
+  const int ldr = even(c->sDr[j]);
+  P.B = c->Lf(j); P.ldB = d * ldr;
+  // pair grouping of bond j (sites j, j+1): matrix chosen by p = g / d
+  P.gs = GroupSpec{c->perm + (size_t)j * c->N, c->goff + (size_t)j * (G + 1), G, d, (long long)ldr, 0};
+  P.e_in = c->emax_slot(j); P.cume_in = c->cume_slot(j);
+  P.e_out = c->emax_slot(j + 1); P.cume_out = c->cume_slot(j + 1);
+  int r = launch_advance(c, P, c->N);
+  if (r != BM_OK) return r;
+  c->vl = j + 1;
+  if (c->vr <= j + 1) c->vr = j + 2;
+  return BM_OK;
+}
+
+// site j applied to the right environment of bond j+1 -> right environment of bond j
+int adv_left(bm_ctx* c, int j) {
+  const int d = c->d, G = d * d;
+  AdvParams P{};
+  P.Ein = c->slot(j + 1); P.ldin = c->ldcap; P.Din = c->sDr[j];
+  P.Eout = c->slot(j); P.ldout = c->ldcap; P.Dout = c->sDl[j];
+  const int ldl = even(c->sDl[j]);
+  P.B = c->Rf(j); P.ldB = d * ldl;
+  // pair grouping of bond j-1 (sites j-1, j): matrix chosen by q = g % d
+  P.gs = GroupSpec{c->perm + (size_t)(j - 1) * c->N, c->goff + (size_t)(j - 1) * (G + 1), G, d, 0, (long long)ldl};
+  P.e_in = c->emax_slot(j + 1); P.cume_in = c->cume_slot(j + 1);
+  P.e_out = c->emax_slot(j); P.cume_out = c->cume_slot(j);
+  int r = launch_advance(c, P, c->N);
+  if (r != BM_OK) return r;
+  c->vr = j;
+  if (c->vl >= j) c->vl = j - 1;
+  return BM_OK;
+}
+
+void invalidate_site(bm_ctx* c, int s) {
+  c->vl = std::min(c->vl, s);
+  c->vr = std::max(c->vr, s + 1);
+}
+
+int chain_alloc(bm_ctx* c, int n) {
+  Chain& ch = c->chain;
+  if (ch.n == n) return BM_OK;
+  for (int i = 0; i < 2; ++i) {
+    DALLOC(ch.V[i], (size_t)n * c->ldcap);
+    DALLOC(ch.e[i], n);
+    DALLOC(ch.cume[i], n);
+    DALLOC(ch.norm[i], n);
+  }
+  DALLOC(ch.phys, (size_t)c->L * n);
+  DALLOC(ch.perm, n);
+  DALLOC(ch.goff, c->d + 1);
+  DALLOC(ch.lnabs, n);
+  DALLOC(ch.sign, n);
+  ch.n = n;
+  return BM_OK;
+}
+
+// upload pixels [n][L] and embed into ch.phys [L][n]
+int chain_upload(bm_ctx* c, const uint8_t* pixels_host, int n) {
+  Chain& ch = c->chain;
+  size_t bytes = (size_t)n * c->L;
+  int r = ensure_stage(c, (bytes + 7) / 8);
+  if (r != BM_OK) return r;
+  CU(cudaMemcpyAsync(c->stage, pixels_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  dim3 grid((c->L + 31) / 32, (n + 31) / 32), block(32, 8);
+  k_embed<<<grid, block, 0, c->stream>>>((const uint8_t*)c->stage, n, c->L, c->d, ch.phys);
+  c->launches++;
+  KCHECK();
+  return BM_OK;
+}
+
+// left chain over sites [0, upto) on chain data; result in ch.V[cur]; returns cur through *cur_out
+int chain_run(bm_ctx* c, int n, int upto, int* cur_out) {
+  Chain& ch = c->chain;
+  const int d = c->d;
+  int cur = 0;
+  k_init_boundary<<<(n + 255) / 256, 256, 0, c->stream>>>(ch.V[0], c->ldcap, n, ch.e[0], ch.cume[0]);
+  c->launches++;
+  for (int j = 0; j < upto; ++j) {
+    k_build_perm<<<1, 256, 0, c->stream>>>(ch.phys + (size_t)j * n, n, d, 0, nullptr, n, ch.perm, ch.goff, n);
+    c->launches++;
+    AdvParams P{};
+    P.Ein = ch.V[cur]; P.ldin = c->ldcap; P.Din = c->sDl[j];
+    P.Eout = ch.V[cur ^ 1]; P.ldout = c->ldcap; P.Dout = c->sDr[j];
+    const int ldr = even(c->sDr[j]);
+    P.B = c->Lf(j); P.ldB = d * ldr;
+    P.gs = GroupSpec{ch.perm, ch.goff, d, 1, (long long)ldr, 0};
+    P.e_in = ch.e[cur]; P.cume_in = ch.cume[cur];
+    P.e_out = ch.e[cur ^ 1]; P.cume_out = ch.cume[cur ^ 1];
+    int r = launch_advance(c, P, n);
+    if (r != BM_OK) return r;
+    cur ^= 1;
+  }
+  KCHECK();
+  *cur_out = cur;
+  return BM_OK;
+}
+
+int check_bond(bm_ctx* c, int k) {
+  REQUIRE(k >= 0 && k < c->L - 1, "bond index out of range");
+  REQUIRE(c->sDl[k] > 0 && c->sDl[k + 1] > 0, "site tensors not set");
+  REQUIRE(c->sDr[k] == c->sDl[k + 1], "bond dimension mismatch between neighbouring sites");
+  return BM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int bm_version(void) { return 100; }
+
+const char* bm_last_error(bm_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+long long bm_launch_count(bm_ctx* c) { return c ? c->launches : 0; }
+void* bm_stream(bm_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_cap, void* stream) {
+  if (!out) return BM_EINVAL;
+  *out = nullptr;
+  if (n_sites < 2 || phys_dim < 2 || phys_dim > 4 || max_bond_cap < 1) return BM_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return BM_ECUDA;
+  bm_ctx* c = new bm_ctx();
+  c->device = device; c->L = n_sites; c->d = phys_dim; c->Dcap = max_bond_cap; c->ldcap = even(max_bond_cap);
+  c->stream = (cudaStream_t)stream;
+  *out = c;   // returned even on failure so that bm_last_error works; caller must bm_destroy
+  CU(cudaSetDevice(device));
+  LIB(cublasCreate(&c->cublas));
+  LIB(cublasSetStream(c->cublas, c->stream));
+  LIB(cusolverDnCreate(&c->cusolver));
+  LIB(cusolverDnSetStream(c->cusolver, c->stream));
+  LIB(cusolverDnCreateGesvdjInfo(&c->gesvdj));
+  LIB(cusolverDnXgesvdjSetTolerance(c->gesvdj, 1e-14));
+  LIB(cusolverDnXgesvdjSetMaxSweeps(c->gesvdj, 100));
+  int r = set_func_attrs(c);
+  if (r != BM_OK) return r;
+  c->site_stride = (size_t)c->Dcap * c->d * c->ldcap;
+  DALLOC(c->Lform, c->site_stride * c->L);
+  DALLOC(c->Rform, c->site_stride * c->L);
+  c->sDl.assign(c->L, 0); c->sDr.assign(c->L, 0);
+  const size_t mA = (size_t)c->d * c->Dcap, ldA = (size_t)c->d * c->ldcap;
+  DALLOC(c->Aint, mA * ldA); DALLOC(c->A2, mA * ldA); DALLOC(c->G, mA * ldA + 2);
+  DALLOC(c->W, mA * mA); DALLOC(c->U, mA * mA); DALLOC(c->V, mA * mA); DALLOC(c->Ssv, mA); DALLOC(c->sgn, mA);
+  DALLOC(c->info, 1); DALLOC(c->iscal, 4);
+  DALLOC(c->partZ, RED_BLOCKS); DALLOC(c->part2, RED_BLOCKS * 4); DALLOC(c->scal, 8);
+  CU(cudaMallocHost((void**)&c->h_scal, 8 * sizeof(double)));
+  CU(cudaMallocHost((void**)&c->h_iscal, 4 * sizeof(int)));
+  CU(cudaMemsetAsync(c->scal, 0, 8 * sizeof(double), c->stream));
+  return BM_OK;
+}
+
+int bm_destroy(bm_ctx* c) {
+  if (!c) return BM_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
+                  c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
+                  c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
+                  c->chain.goff, c->chain.U, c->chain.lnabs, c->chain.sign};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->h_iscal) cudaFreeHost(c->h_iscal);
+  if (c->tev[0]) { cudaEventDestroy(c->tev[0]); cudaEventDestroy(c->tev[1]); }
+  if (c->gesvdj) cusolverDnDestroyGesvdjInfo(c->gesvdj);
+  if (c->cusolver) cusolverDnDestroy(c->cusolver);
+  if (c->cublas) cublasDestroy(c->cublas);
+  delete c;
+  return BM_OK;
+}
+
+int bm_set_timing(bm_ctx* c, int on) {
+  if (!c) return BM_EINVAL;
+  CU(cudaSetDevice(c->device));
+  if (on && !c->tev[0]) { CU(cudaEventCreate(&c->tev[0])); CU(cudaEventCreate(&c->tev[1])); }
+  c->timing = on ? 1 : 0;
+  for (int i = 0; i < 8; ++i) { c->t_ms[i] = 0; c->t_n[i] = 0; }
+  return BM_OK;
+}
+
+int bm_get_timing(bm_ctx* c, double* ms8, long long* n8) {
+  if (!c || !ms8 || !n8) return BM_EINVAL;
+  for (int i = 0; i < 8; ++i) { ms8[i] = c->t_ms[i]; n8[i] = c->t_n[i]; }
+  return BM_OK;
+}
+
+int bm_set_svd(bm_ctx* c, int method) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(method == BM_SVD_GESVDJ || method == BM_SVD_GRAM, "unsupported SVD method");
+  c->svd_method = method;
+  return BM_OK;
+}
+
+int bm_set_data(bm_ctx* c, const uint8_t* pixels_host, int n) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(pixels_host && n > 0, "bm_set_data: bad arguments");
+  CU(cudaSetDevice(c->device));
+  const int L = c->L, d = c->d, G = d * d;
+  c->N = n;
+  DALLOC(c->phys, (size_t)L * n);
+  DALLOC(c->perm, (size_t)(L - 1) * n);
+  DALLOC(c->goff, (size_t)(L - 1) * (G + 1));
+  DALLOC(c->bperm, n); DALLOC(c->bgoff, G + 1); DALLOC(c->bmask, n);
+  size_t bytes = (size_t)n * L;
+  int r = ensure_stage(c, (bytes + 7) / 8);
+  if (r != BM_OK) return r;
+  CU(cudaMemcpyAsync(c->stage, pixels_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  dim3 grid((L + 31) / 32, (n + 31) / 32), block(32, 8);
+  k_embed<<<grid, block, 0, c->stream>>>((const uint8_t*)c->stage, n, L, d, c->phys);
+  k_build_perm<<<L - 1, 256, 0, c->stream>>>(c->phys, n, d, 1, nullptr, n, c->perm, c->goff, n);
+  c->launches += 2;
+  KCHECK();
+  c->h_goff.resize((size_t)(L - 1) * (G + 1));
+  CU(cudaMemcpyAsync(c->h_goff.data(), c->goff, c->h_goff.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  // environment stack: one slot per bond 0..L
+  c->slot_stride = (size_t)n * c->ldcap;
+  DALLOC(c->E, c->slot_stride * (L + 1));
+  DALLOC(c->emax, (size_t)n * (L + 1));
+  DALLOC(c->cume, (size_t)n * (L + 1));
+  DALLOC(c->psi, n); DALLOC(c->winv, n); DALLOC(c->lnpsi, n);
+  k_init_boundary<<<(n + 255) / 256, 256, 0, c->stream>>>(c->slot(0), c->ldcap, n, c->emax_slot(0), c->cume_slot(0));
+  k_init_boundary<<<(n + 255) / 256, 256, 0, c->stream>>>(c->slot(L), c->ldcap, n, c->emax_slot(L), c->cume_slot(L));
+  c->launches += 2;
+  KCHECK();
+  c->vl = 0; c->vr = L;
+  // gradient split workspace: enough slots for one group holding every sample
+  {
+    const int tiles = ((c->Dcap + GT - 1) / GT) * ((c->Dcap + GT - 1) / GT);
+    long long work = (long long)n * tiles;
+    int kchunk = (int)((work + 2 * 148 - 1) / (2 * 148));
+    kchunk = std::max(KC, std::min(GRAD_MAXCHUNK, ((kchunk + KC - 1) / KC) * KC));
+    c->last_kchunk = kchunk;
+    c->ws_slots = (n + kchunk - 1) / kchunk;
+    DALLOC(c->ws, (size_t)c->ws_slots * c->d * c->Dcap * c->d * c->ldcap);
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < L - 1; ++b)
+    REQUIRE(c->h_goff[(size_t)b * (G + 1) + G] == n, "bm_set_data: training images must not contain unknown pixels");
+  return BM_OK;
+}
+
+int bm_set_site(bm_ctx* c, int k, const double* lrp_host, int Dl, int Dr) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(k >= 0 && k < c->L && lrp_host, "bm_set_site: bad arguments");
+  REQUIRE(Dl >= 1 && Dr >= 1 && Dl <= c->Dcap && Dr <= c->Dcap, "bm_set_site: bond dimension exceeds max_bond_cap");
+  REQUIRE((k != 0 || Dl == 1) && (k != c->L - 1 || Dr == 1), "bm_set_site: boundary sites need an outer bond of 1");
+  CU(cudaSetDevice(c->device));
+  size_t cnt = (size_t)Dl * Dr * c->d;
+  int r = ensure_stage(c, cnt);
+  if (r != BM_OK) return r;
+  CU(cudaMemcpyAsync(c->stage, lrp_host, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_site_from_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(c->stage, c->d, Dl, Dr, c->Lf(k), c->Rf(k));
+  c->launches++;
+  KCHECK();
+  CU(cudaStreamSynchronize(c->stream));   // lrp_host may be pageable and freed by the caller
+  c->sDl[k] = Dl; c->sDr[k] = Dr;
+  invalidate_site(c, k);
+  return BM_OK;
+}
+
+int bm_site_dims(bm_ctx* c, int k, int* Dl, int* Dr) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(k >= 0 && k < c->L, "bm_site_dims: bad site");
+  if (Dl) *Dl = c->sDl[k];
+  if (Dr) *Dr = c->sDr[k];
+  return BM_OK;
+}
+
+int bm_get_site(bm_ctx* c, int k, double* lrp_host, int* Dl, int* Dr) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(k >= 0 && k < c->L && lrp_host, "bm_get_site: bad arguments");
+  REQUIRE(c->sDl[k] > 0, "bm_get_site: site not set");
+  CU(cudaSetDevice(c->device));
+  size_t cnt = (size_t)c->sDl[k] * c->sDr[k] * c->d;
+  int r = ensure_stage(c, cnt);
+  if (r != BM_OK) return r;
+  k_site_to_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(c->Lf(k), c->d, c->sDl[k], c->sDr[k], c->stage);
+  c->launches++;
+  KCHECK();
+  CU(cudaMemcpyAsync(lrp_host, c->stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (Dl) *Dl = c->sDl[k];
+  if (Dr) *Dr = c->sDr[k];
+  return BM_OK;
+}
+
+int bm_env_build(bm_ctx* c, int k) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->N > 0, "bm_env_build: no training data");
+  REQUIRE(k >= 0 && k < c->L - 1, "bm_env_build: bond out of range");
+  for (int j = 0; j < c->L - 1; ++j) REQUIRE(c->sDl[j] > 0 && c->sDr[j] == c->sDl[j + 1], "bm_env_build: MPS not fully set / inconsistent bonds");
+  CU(cudaSetDevice(c->device));
+  while (c->vl < k) { int r = adv_right(c, c->vl); if (r != BM_OK) return r; }
+  while (c->vr > k + 2) { int r = adv_left(c, c->vr - 1); if (r != BM_OK) return r; }
+  return BM_OK;
+}
+
+int bm_env_advance(bm_ctx* c, int k, int going_right) {
+  if (!c) return BM_EINVAL;
+  int r = check_bond(c, k);
+  if (r != BM_OK) return r;
+  CU(cudaSetDevice(c->device));
+  if (going_right) {
+    REQUIRE(c->vl >= k, "bm_env_advance: left environment of bond k is not valid");
+    c->vl = k;
+    return adv_right(c, k);
+  }
+  REQUIRE(c->vr <= k + 2, "bm_env_advance: right environment of bond k+2 is not valid");
+  c->vr = k + 2;
+  return adv_left(c, k + 1);
+}
+
+int bm_env_get(bm_ctx* c, int side, int j, double* out_host, int* D) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(j >= 0 && j <= c->L && out_host, "bm_env_get: bad arguments");
+  REQUIRE(side == 0 ? j <= c->vl : j >= c->vr, "bm_env_get: that environment is not valid");
+  CU(cudaSetDevice(c->device));
+  int Dj = (j == 0 || j == c->L) ? 1 : c->sDl[j];
+  size_t cnt = (size_t)c->N * Dj;
+  int r = ensure_stage(c, cnt);
+  if (r != BM_OK) return r;
+  k_env_export<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->slot(j), c->ldcap, Dj, c->N, c->stage);
+  c->launches++;
+  KCHECK();
+  CU(cudaMemcpyAsync(out_host, c->stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (D) *D = Dj;
+  return BM_OK;
+}
+
+int bm_grad_dims(bm_ctx* c, int k, int* rows, int* ld, int* Dl, int* Dr, int* ldR) {
+  if (!c) return BM_EINVAL;
+  int r = check_bond(c, k);
+  if (r != BM_OK) return r;
+  int dl = c->sDl[k], dr = c->sDr[k + 1], ldr = even(dr);
+  if (rows) *rows = c->d * dl;
+  if (ld) *ld = c->d * ldr;
+  if (Dl) *Dl = dl;
+  if (Dr) *Dr = dr;
+  if (ldR) *ldR = ldr;
+  return BM_OK;
+}
+
+int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double* S_dev) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->N > 0 && S_dev, "bm_step_grad: no training data / null output");
+  int r = check_bond(c, k);
+  if (r != BM_OK) return r;
+  r = bm_env_build(c, k);
+  if (r != BM_OK) return r;
+  const int d = c->d, G = d * d, N = c->N;
+  const int Dl = c->sDl[k], chi0 = c->sDr[k], Dr = c->sDr[k + 1];
+  const int ldx = even(chi0), ldr = even(Dr), ldA = d * ldr, rows = d * Dl;
+
+  // ---- merge: A[(p,a),(q,c)] = sum_b M_k[a,b,p] M_{k+1}[b,c,q]  (TNutils.py:1526) — plain library GEMMs
+  {
+    Timer t_(c, 4);
+    const double one = 1.0, zero = 0.0;
+    for (int p = 0; p < d; ++p)
+      for (int q = 0; q < d; ++q) {
+        const double* X = c->Lf(k) + (size_t)p * ldx;        // [a][p][b], ld = d*ldx
+        const double* Y = c->Rf(k + 1) + (size_t)q * ldx;    // [c][q][b], ld = d*ldx
+        double* C = c->Aint + (size_t)p * Dl * ldA + (size_t)q * ldr;
+        LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, Dr, Dl, chi0, &one, Y, d * ldx, X, d * ldx, &zero, C, ldA));
+      }
+  }
+  k_sumsq<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, rows, ldA, Dr, ldr, c->partZ);
+  c->launches++;
+
+  // ---- grouping for this step: all samples (precomputed) or a minibatch
+  const int* perm; const int* goff; const int* h_goff; int B;
+  if (mask_host) {
+    REQUIRE(n_mask > 0 && n_mask <= N, "bm_step_grad: bad minibatch size");
+    CU(cudaMemcpyAsync(c->bmask, mask_host, (size_t)n_mask * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_build_perm<<<1, 256, 0, c->stream>>>(c->phys + (size_t)k * N, N, d, 1, c->bmask, n_mask, c->bperm, c->bgoff, N);
+    c->launches++;
+    c->h_bgoff.resize(G + 1);
+    CU(cudaMemcpyAsync(c->h_bgoff.data(), c->bgoff, (G + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    perm = c->bperm; goff = c->bgoff; h_goff = c->h_bgoff.data(); B = n_mask;
+  } else {
+    perm = c->perm + (size_t)k * N; goff = c->goff + (size_t)k * (G + 1); h_goff = c->h_goff.data() + (size_t)k * (G + 1); B = N;
+  }
+
+  // ---- psi
+  {
+    Timer t_(c, 1);
+    PsiParams P{};
+    P.Lenv = c->slot(k); P.ldL = c->ldcap; P.Dl = Dl;
+    P.Renv = c->slot(k + 2); P.ldR = c->ldcap; P.Dr = Dr;
+    P.A = c->Aint; P.ldA = ldA;
+    P.gs = GroupSpec{perm, goff, G, d, (long long)Dl * ldA, (long long)ldr};
+    P.cumeL = c->cume_slot(k); P.cumeR = c->cume_slot(k + 2);
+    P.psi = c->psi; P.winv = c->winv; P.lnpsi = c->lnpsi;
+    int tm = pick_tm(B), grid = max_tiles(B, tm, G);
+    if (tm == 64) k_psi<64><<<grid, NTHREADS, panel_smem<64>(), c->stream>>>(P);
+    else if (tm == 32) k_psi<32><<<grid, NTHREADS, panel_smem<32>(), c->stream>>>(P);
+    else k_psi<16><<<grid, NTHREADS, panel_smem<16>(), c->stream>>>(P);
+    c->launches++;
+    KCHECK();
+  }
+  // ---- gradient accumulation
+  {
+    const int tiles_a = (Dl + GT - 1) / GT, tiles_c = (Dr + GT - 1) / GT;
+    int maxg = 0;
+    for (int g = 0; g < G; ++g) maxg = std::max(maxg, h_goff[g + 1] - h_goff[g]);
+    long long work = (long long)B * tiles_a * tiles_c;
+    int kchunk = (int)((work + 2 * 148 - 1) / (2 * 148));
+    kchunk = std::max(KC, std::min(GRAD_MAXCHUNK, ((kchunk + KC - 1) / KC) * KC));
+    int nsplit = (maxg + kchunk - 1) / kchunk;
+    while (nsplit > c->ws_slots) { kchunk += KC; nsplit = (maxg + kchunk - 1) / kchunk; }
+    REQUIRE(kchunk <= GRAD_MAXCHUNK, "bm_step_grad: gradient workspace too small");
+    GradParams P{};
+    P.Lenv = c->slot(k); P.ldL = c->ldcap; P.Dl = Dl;
+    P.Renv = c->slot(k + 2); P.ldR = c->ldcap; P.Dr = Dr;
+    P.winv = c->winv; P.perm = perm; P.goff = goff; P.ngroups = G; P.d = d;
+    P.kchunk = kchunk; P.ws = c->ws; P.ws_stride = (long long)rows * ldA; P.ldA = ldA; P.ldRpad = ldr; P.tiles_c = tiles_c;
+    dim3 grid(std::max(nsplit, 1), tiles_a * tiles_c, G);
+    { Timer t_(c, 2); k_grad<<<grid, NTHREADS, sizeof(GradSmem), c->stream>>>(P); }
+    { Timer t_(c, 3); k_grad_reduce<<<148 * 4, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, S_dev); }
+    k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, S_dev + (size_t)rows * ldA);
+    c->launches += 3;
+    KCHECK();
+  }
+  c->last_k = k; c->last_B = B; c->last_ids = perm;
+  return BM_OK;
+}
+
+// thin SVD of W (column-major mA x nA) -> Ssv, U (mA x r), V (nA x r)
+static int run_svd(bm_ctx* c, int mA, int nA) {
+  Timer t_(c, 5);
+  if (c->svd_method == BM_SVD_GESVDJ) {
+    int lw = 0;
+    LIB(cusolverDnDgesvdj_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, 1, mA, nA, c->W, mA, c->Ssv, c->U, mA, c->V, nA, &lw, c->gesvdj));
+    if ((size_t)lw > c->lwork) { DALLOC(c->work, (size_t)lw); c->lwork = (size_t)lw; }
+    LIB(cusolverDnDgesvdj(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, 1, mA, nA, c->W, mA, c->Ssv, c->U, mA, c->V, nA, c->work, lw, c->info, c->gesvdj));
+    return BM_OK;
+  }
+  return fail(c, BM_EINVAL, "SVD method not implemented");
+}
+
+int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
+                   int going_right, int max_bond, double cutoff, double mom_bias,
+                   double* scalars_host, double* s_host) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(k == c->last_k, "bm_step_update: call bm_step_grad for the same bond first");
+  REQUIRE(S_dev && batch_total > 0, "bm_step_update: bad arguments");
+  REQUIRE(renorm == BM_RENORM_MAX || renorm == BM_RENORM_L2, "bm_step_update: bad renorm");
+  CU(cudaSetDevice(c->device));
+  const int d = c->d;
+  const int Dl = c->sDl[k], Dr = c->sDr[k + 1];
+  const int ldr = even(Dr), ldA = d * ldr, rows = d * Dl, ncols = d * Dr;
+  const int rmin = std::min(rows, ncols);
+  if (max_bond > c->Dcap || max_bond <= 0) max_bond = std::min(c->Dcap, max_bond > 0 ? max_bond : c->Dcap);
+
+  // zero-psi check before touching anything (TNutils.py:1244-1254)
+  CU(cudaMemcpyAsync(c->h_scal, S_dev + (size_t)rows * ldA, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const double sumln = c->h_scal[0], nzero = c->h_scal[1];
+  if (nzero > 0) {
+    if (scalars_host) { std::memset(scalars_host, 0, 8 * sizeof(double)); scalars_host[1] = sumln; scalars_host[2] = nzero; }
+    return fail(c, BM_EZERO_PSI, "psi == 0 for " + std::to_string((long long)nzero) + " samples; update skipped");
+  }
+
+  k_update<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, S_dev, c->partZ, rows, ldA, Dr, ldr, batch_total, lr, mom_bias, c->A2, c->part2, c->scal);
+  k_scale_to_colmajor<<<RED_BLOCKS * 4, 256, 0, c->stream>>>(c->A2, c->part2, rows, ldA, d, Dr, ldr, renorm, c->W, c->scal);
+  c->launches += 2;
+  KCHECK();
+  int r = run_svd(c, rows, ncols);
+  if (r != BM_OK) return r;
+  k_chi<<<1, 32, 0, c->stream>>>(c->Ssv, rmin, cutoff, max_bond, c->info, c->iscal, c->scal);
+  c->launches++;
+  CU(cudaMemcpyAsync(c->h_iscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_scal, c->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (s_host) CU(cudaMemcpyAsync(s_host, c->Ssv, (size_t)rmin * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  k_gauge_signs<<<32, 256, 0, c->stream>>>(c->U, rows, d, Dl, c->iscal, c->sgn);
+  c->launches++;
+  k_factor_out<<<148 * 2, 256, 0, c->stream>>>(c->U, c->V, c->Ssv, c->sgn, c->iscal, d, Dl, Dr, going_right ? 1 : 0,
+                                               c->Lf(k), c->Rf(k), c->Lf(k + 1), c->Rf(k + 1));
+  c->launches++;
+  KCHECK();
+  CU(cudaStreamSynchronize(c->stream));
+  const int chi = c->h_iscal[0], info = c->h_iscal[1];
+  if (scalars_host) {
+    std::memcpy(scalars_host, c->h_scal, 8 * sizeof(double));
+    scalars_host[1] = sumln; scalars_host[2] = nzero; scalars_host[3] = chi;
+  }
+  c->sDr[k] = chi; c->sDl[k + 1] = chi;
+  invalidate_site(c, k); invalidate_site(c, k + 1);
+  c->last_k = -1;
+  if (c->h_scal[7] > 0) return fail(c, BM_ENONFINITE, "non-finite entries in the updated merged tensor");
+  if (info != 0) return fail(c, BM_ECUSOLVER, "SVD did not converge (info=" + std::to_string(info) + ")");
+  return BM_OK;
+}
+
+int bm_get_merged(bm_ctx* c, double* A_host) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->last_k >= 0 && A_host, "bm_get_merged: no merged tensor available");
+  return bm_engine_to_ref(c, c->last_k, c->Aint, A_host);
+}
+
+int bm_engine_to_ref(bm_ctx* c, int k, const double* eng_dev, double* ref_host) {
+  if (!c) return BM_EINVAL;
+  int r = check_bond(c, k);
+  if (r != BM_OK) return r;
+  REQUIRE(eng_dev && ref_host, "bm_engine_to_ref: null pointer");
+  CU(cudaSetDevice(c->device));
+  const int d = c->d, Dl = c->sDl[k], Dr = c->sDr[k + 1], ldr = even(Dr);
+  size_t cnt = (size_t)Dl * d * Dr * d;
+  r = ensure_stage(c, cnt);
+  if (r != BM_OK) return r;
+  k_engine_to_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(eng_dev, d, Dl, Dr, d * ldr, ldr, c->stage);
+  c->launches++;
+  KCHECK();
+  CU(cudaMemcpyAsync(ref_host, c->stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BM_OK;
+}
+
+int bm_ref_to_engine(bm_ctx* c, int k, const double* ref_host, double* eng_dev) {
+  if (!c) return BM_EINVAL;
+  int r = check_bond(c, k);
+  if (r != BM_OK) return r;
+  REQUIRE(eng_dev && ref_host, "bm_ref_to_engine: null pointer");
+  CU(cudaSetDevice(c->device));
+  const int d = c->d, Dl = c->sDl[k], Dr = c->sDr[k + 1], ldr = even(Dr);
+  size_t cnt = (size_t)Dl * d * Dr * d;
+  r = ensure_stage(c, cnt);
+  if (r != BM_OK) return r;
+  CU(cudaMemcpyAsync(c->stage, ref_host, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(eng_dev, 0, (size_t)d * Dl * d * ldr * sizeof(double), c->stream));
+  k_ref_to_engine<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(c->stage, d, Dl, Dr, d * ldr, ldr, eng_dev);
+  c->launches++;
+  KCHECK();
+  CU(cudaStreamSynchronize(c->stream));
+  return BM_OK;
+}
+
+int bm_last_logpsi(bm_ctx* c, double* lnabs_host) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->N > 0 && lnabs_host, "bm_last_logpsi: bad arguments");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(lnabs_host, c->lnpsi, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BM_OK;
+}
+
+int bm_logpsi(bm_ctx* c, const uint8_t* pixels_host, int n, double* lnabs_host, double* sign_host) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(pixels_host && n > 0 && lnabs_host, "bm_logpsi: bad arguments");
+  for (int j = 0; j < c->L; ++j) REQUIRE(c->sDl[j] > 0 && (j == c->L - 1 || c->sDr[j] == c->sDl[j + 1]), "bm_logpsi: MPS not fully set");
+  CU(cudaSetDevice(c->device));
+  int r = chain_alloc(c, n);
+  if (r != BM_OK) return r;
+  r = chain_upload(c, pixels_host, n);
+  if (r != BM_OK) return r;
+  int cur = 0;
+  r = chain_run(c, n, c->L, &cur);
+  if (r != BM_OK) return r;
+  Chain& ch = c->chain;
+  k_finish_logpsi<<<(n + 255) / 256, 256, 0, c->stream>>>(ch.V[cur], c->ldcap, ch.cume[cur], n, ch.lnabs, ch.sign);
+  c->launches++;
+  KCHECK();
+  CU(cudaMemcpyAsync(lnabs_host, ch.lnabs, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (sign_host) CU(cudaMemcpyAsync(sign_host, ch.sign, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BM_OK;
+}
+
+// shared sampling loop; pixels land in ch.phys (as physical indices until converted)
+static int sample_loop(bm_ctx* c, int n, int rule, int start_site, const double* U_host, uint64_t seed, int cur) {
+  Chain& ch = c->chain;
+  const int d = c->d, L = c->L;
+  const int first_phys = rule == BM_RULE_BATCHED ? 0 : 1;
+  const size_t nsites = (size_t)(L - start_site);
+  if (U_host) {
+    if (ch.Ucap < nsites * n) { DALLOC(ch.U, nsites * n); ch.Ucap = nsites * n; }
+    CU(cudaMemcpyAsync(ch.U, U_host, nsites * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  } else if (ch.Ucap < (size_t)n) { DALLOC(ch.U, n); ch.Ucap = n; }
+  const int tm = pick_tm(n), grid = (n + tm - 1) / tm;
+  for (int s = start_site; s < L; ++s) {
+    const double* Us = ch.U;
+    if (U_host) Us = ch.U + (size_t)(s - start_site) * n;
+    else { k_fill_uniform<<<(n + 255) / 256, 256, 0, c->stream>>>(ch.U, n, seed, s); c->launches++; }
+    SampleParams P{};
+    P.Vin = ch.V[cur]; P.ldv = c->ldcap; P.Din = c->sDl[s];
+    P.Vout = ch.V[cur ^ 1]; P.Dout = c->sDr[s];
+    const int ldr = even(c->sDr[s]);
+    P.Bfirst = c->Lf(s) + (size_t)first_phys * ldr;
+    P.Bsecond = c->Lf(s) + (size_t)(1 - first_phys) * ldr;
+    P.ldB = d * ldr;
+    P.norm_in = ch.norm[cur]; P.e_in = ch.e[cur];
+    P.norm_out = ch.norm[cur ^ 1]; P.e_out = ch.e[cur ^ 1];
+    P.U = Us; P.pix_out = ch.phys + (size_t)s * n;
+    P.n = n; P.strict = rule == BM_RULE_SINGLE; P.pix_first = rule == BM_RULE_BATCHED ? 1 : 0;
+    P.both_norm = (s == start_site);
+    {
+      Timer t_(c, 7);
+      if (tm == 64) k_sample_step<64><<<grid, NTHREADS, panel_smem<64>(), c->stream>>>(P);
+      else if (tm == 32) k_sample_step<32><<<grid, NTHREADS, panel_smem<32>(), c->stream>>>(P);
+      else k_sample_step<16><<<grid, NTHREADS, panel_smem<16>(), c->stream>>>(P);
+    }
+    c->launches++;
+    cur ^= 1;
+  }
+  KCHECK();
+  return BM_OK;
+}
+
+int bm_sample(bm_ctx* c, int n, int rule, int start_site, const double* U_host, uint64_t seed,
+              const uint8_t* prefix_pixels_host, uint8_t* out_host) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->d == 2, "bm_sample: the reference samplers are defined for binary pixels (d=2) only");
+  REQUIRE(n > 0 && out_host && start_site >= 0 && start_site < c->L, "bm_sample: bad arguments");
+  REQUIRE(rule == BM_RULE_BATCHED || rule == BM_RULE_SINGLE, "bm_sample: bad rule");
+  REQUIRE(start_site == 0 || prefix_pixels_host, "bm_sample: a known prefix needs prefix_pixels_host");
+  for (int j = 0; j < c->L; ++j) REQUIRE(c->sDl[j] > 0 && (j == c->L - 1 || c->sDr[j] == c->sDl[j + 1]), "bm_sample: MPS not fully set");
+  CU(cudaSetDevice(c->device));
+  int r = chain_alloc(c, n);
+  if (r != BM_OK) return r;
+  Chain& ch = c->chain;
+  int cur = 0;
+  if (start_site > 0) {
+    r = chain_upload(c, prefix_pixels_host, n);
+    if (r != BM_OK) return r;
+    r = chain_run(c, n, start_site, &cur);
+    if (r != BM_OK) return r;
+    k_rownorm2<<<(n + 127) / 128, 128, 0, c->stream>>>(ch.V[cur], c->ldcap, c->sDl[start_site], n, ch.norm[cur]);
+    k_phys_to_pix<<<(int)(((size_t)start_site * n + 255) / 256), 256, 0, c->stream>>>(ch.phys, (long long)start_site * n, c->d);
+    c->launches += 2;
+  } else {
+    k_init_boundary<<<(n + 255) / 256, 256, 0, c->stream>>>(ch.V[0], c->ldcap, n, ch.e[0], ch.cume[0]);
+    c->launches++;
+  }
+  r = sample_loop(c, n, rule, start_site, U_host, seed, cur);
+  if (r != BM_OK) return r;
+  size_t bytes = (size_t)n * c->L;
+  r = ensure_stage(c, (bytes + 7) / 8);
+  if (r != BM_OK) return r;
+  dim3 grid((c->L + 31) / 32, (n + 31) / 32), block(32, 8);
+  k_unembed<<<grid, block, 0, c->stream>>>(ch.phys, n, c->L, c->d, (uint8_t*)c->stage);
+  c->launches++;
+  KCHECK();
+  CU(cudaMemcpyAsync(out_host, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BM_OK;
+}
+
+int bm_sample_device(bm_ctx* c, int n, int rule, uint64_t seed, float* ms) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->d == 2 && n > 0, "bm_sample_device: bad arguments");
+  for (int j = 0; j < c->L; ++j) REQUIRE(c->sDl[j] > 0 && (j == c->L - 1 || c->sDr[j] == c->sDl[j + 1]), "bm_sample_device: MPS not fully set");
+  CU(cudaSetDevice(c->device));
+  int r = chain_alloc(c, n);
+  if (r != BM_OK) return r;
+  Chain& ch = c->chain;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, c->stream));
+  k_init_boundary<<<(n + 255) / 256, 256, 0, c->stream>>>(ch.V[0], c->ldcap, n, ch.e[0], ch.cume[0]);
+  c->launches++;
+  r = sample_loop(c, n, rule, 0, nullptr, seed, 0);
+  if (r != BM_OK) return r;
+  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaEventSynchronize(e1));
+  float t = 0;
+  CU(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ms) *ms = t;
+  return BM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,903 @@
+// bm_kernels.cuh — sm_100a device code of libbm.so (FP64 family).
+//
+// tcgen05.mma has no FP64 kind, so the FP64 path runs on DMMA.8x8x4 (mma.sync.m8n8k4.f64), measured at
+// 37.1 TFLOP/s on this B200 (profiles/r01_probe_fp64_svd.jsonl); operands are staged global->shared with
+// 16-byte cp.async (LDGSTS) in a 3-stage ring and read as conflict-free 8x4 / 4x8 fragments.
+//
+// Every hot kernel is a "row panel" GEMM: rows are samples (gathered through a pixel-pair permutation so
+// that all rows of a tile use the same site matrix), columns are bond indices.
+//   k_env_advance : E_out[n,:] = (E_in[n,:] . M[x_n]) * 2^-e_in[n]      (sequential_update, TNutils.py:504-526)
+//   k_psi         : psi_n = (L_n . A[x,y]) . R_n                          (learning_step_cached, :1534)
+//   k_grad        : S[x,y] += L_g^T diag(1/psi) R_g  (split over samples) (:1535-1536, psi' never materialised)
+//   k_sample_step : per-site conditional + branch selection               (generate_samples, :1847-1872)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bm {
+
+constexpr int KC = 16;          // k-chunk (doubles) per pipeline stage
+constexpr int TN = 128;         // column tile
+constexpr int NTHREADS = 256;   // 8 warps arranged 2 (rows) x 4 (cols)
+constexpr int STAGES = 3;
+constexpr int A_STRIDE = KC + 4;   // 20: row stride (doubles) == 4 mod 16 -> conflict-free 8x4 fragment reads
+constexpr int B_STRIDE = TN + 4;   // 132
+constexpr double LN2 = 0.69314718055994530942;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(s), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
+// exponent e with m = f * 2^e, f in [0.5,1); 0 for m == 0 / non-finite.  Clamped to +-1000.
+__device__ __forceinline__ int frexp_exp(double m) {
+  if (!(m > 0.0) || isinf(m)) return 0;
+  long long bits = __double_as_longlong(m);
+  int ef = (int)((bits >> 52) & 0x7ff);
+  if (ef == 0) return -1000;
+  int e = ef - 1022;
+  return max(-1000, min(1000, e));
+}
+__device__ __forceinline__ double pow2d(int e) {   // exact 2^e, e in [-1022,1023]
+  return __longlong_as_double((long long)(e + 1023) << 52);
+}
+
+// Row grouping: rows [goff[g], goff[g+1]) of `perm` share matrix  B + (g / gdiv) * strideHi + (g % gdiv) * strideLo.
+struct GroupSpec {
+  const int* perm;     // sample ids, grouped (nullptr = identity)
+  const int* goff;     // ngroups + 1 offsets into perm
+  int ngroups;
+  int gdiv;
+  long long strideHi, strideLo;
+};
+
+template <int TM> struct PanelSmem {
+  double A[STAGES][TM][A_STRIDE];
+  double B[STAGES][KC][B_STRIDE];
+};
+
+// blockIdx.x -> (group, first row, number of rows); false if this CTA has no tile.
+template <int TM>
+__device__ __forceinline__ bool locate_tile(const GroupSpec& gs, int& g, int& row0, int& nrows) {
+  int t = blockIdx.x;
+  for (g = 0; g < gs.ngroups; ++g) {
+    int ng = gs.goff[g + 1] - gs.goff[g];
+    int nt = (ng + TM - 1) / TM;
+    if (t < nt) break;
+    t -= nt;
+  }
+  if (g >= gs.ngroups) return false;
+  row0 = gs.goff[g] + t * TM;
+  nrows = min(TM, gs.goff[g + 1] - row0);
+  return true;
+}
+
+// acc (TM x TN tile, this thread's fragments) = rows(rowptr)[:, 0:Din] . B[0:Din, col0:col0+TN]
+// B element (k, n) at B[k*ldB + n].  All 256 threads must call.  Requires 16-byte aligned row starts.
+template <int TM>
+__device__ __forceinline__ void panel_gemm(PanelSmem<TM>& sm, const double* const* rowptr, int Din,
+                                           const double* __restrict__ B, int ldB, int col0, int Dout,
+                                           double (&acc)[TM / 16][4][2]) {
+  constexpr int MT = TM / 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int nkc = (Din + KC - 1) / KC;
+
+  auto load = [&](int stage, int kc) {
+    const int k0 = kc * KC;
+    for (int i = tid; i < TM * (KC / 2); i += NTHREADS) {
+      int r = i / (KC / 2), c2 = i % (KC / 2);
+      int k = k0 + c2 * 2;
+      const double* rp = rowptr[r];
+      int valid = rp ? max(0, min(2, Din - k)) : 0;
+      cp_async16(&sm.A[stage][r][c2 * 2], valid ? (const void*)(rp + k) : (const void*)B, valid * 8);
+    }
+    for (int i = tid; i < KC * (TN / 2); i += NTHREADS) {
+      int kk = i / (TN / 2), c2 = i % (TN / 2);
+      int k = k0 + kk, col = col0 + c2 * 2;
+      int valid = (k < Din) ? max(0, min(2, Dout - col)) : 0;
+      cp_async16(&sm.B[stage][kk][c2 * 2], valid ? (const void*)(B + (long long)k * ldB + col) : (const void*)B,
+                 valid * 8);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nkc) load(s, s);
+    cp_async_commit();
+  }
+  for (int kc = 0; kc < nkc; ++kc) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    int nx = kc + STAGES - 1;
+    if (nx < nkc) load(nx % STAGES, nx);
+    cp_async_commit();
+    const int st = kc % STAGES;
+#pragma unroll
+    for (int ks = 0; ks < KC; ks += 4) {
+      double a[MT], b[4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[mt] = sm.A[st][wm * (TM / 2) + mt * 8 + (lane >> 2)][ks + (lane & 3)];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) b[nt] = sm.B[st][ks + (lane & 3)][wn * 32 + nt * 8 + (lane >> 2)];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// environment advance
+// ------------------------------------------------------------------------------------------------
+struct AdvParams {
+  const double* Ein; int ldin; int Din;
+  double* Eout; int ldout; int Dout;
+  const double* B; int ldB;
+  GroupSpec gs;
+  const int* e_in; const int* cume_in;
+  int* e_out; int* cume_out;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(NTHREADS) k_env_advance(AdvParams P) {
+  constexpr int MT = TM / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PanelSmem<TM>& sm = *reinterpret_cast<PanelSmem<TM>*>(smem_raw);
+  __shared__ const double* rowptr[TM];
+  __shared__ int rowid[TM];
+  __shared__ double rscale[TM];
+  __shared__ double rmax[TM][4];
+  int g, row0, nrows;
+  if (!locate_tile<TM>(P.gs, g, row0, nrows)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+  if (tid < TM) {
+    int id = -1;
+    if (tid < nrows) id = P.gs.perm ? P.gs.perm[row0 + tid] : row0 + tid;
+    rowid[tid] = id;
+    rowptr[tid] = id >= 0 ? P.Ein + (long long)id * P.ldin : nullptr;
+    rscale[tid] = id >= 0 ? pow2d(-P.e_in[id]) : 0.0;
+  }
+  __syncthreads();
+  const double* B = P.B + (g / P.gs.gdiv) * P.gs.strideHi + (g % P.gs.gdiv) * P.gs.strideLo;
+  double tmax[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) tmax[i] = 0.0;
+  for (int col0 = 0; col0 < P.Dout; col0 += TN) {
+    double acc[MT][4][2];
+    panel_gemm<TM>(sm, rowptr, P.Din, B, P.ldB, col0, P.Dout, acc);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      int r = wm * (TM / 2) + mt * 8 + (lane >> 2);
+      int id = rowid[r];
+      if (id < 0) continue;
+      double sc = rscale[r];
+      double* orow = P.Eout + (long long)id * P.ldout;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        int col = col0 + wn * 32 + nt * 8 + 2 * (lane & 3);
+        double v0 = acc[mt][nt][0] * sc, v1 = acc[mt][nt][1] * sc;
+        if (col + 1 < P.Dout) {
+          *reinterpret_cast<double2*>(orow + col) = make_double2(v0, v1);
+          tmax[mt] = fmax(tmax[mt], fmax(fabs(v0), fabs(v1)));
+        } else if (col < P.Dout) {
+          orow[col] = v0;
+          tmax[mt] = fmax(tmax[mt], fabs(v0));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    double m = tmax[mt];
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    if ((lane & 3) == 0) rmax[wm * (TM / 2) + mt * 8 + (lane >> 2)][wn] = m;
+  }
+  __syncthreads();
+  if (tid < TM && rowid[tid] >= 0) {
+    int id = rowid[tid];
+    double m = fmax(fmax(rmax[tid][0], rmax[tid][1]), fmax(rmax[tid][2], rmax[tid][3]));
+    P.e_out[id] = frexp_exp(m);
+    P.cume_out[id] = P.cume_in[id] + P.e_in[id];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// psi_n = (L_n . A[p,q]) . R_n   -> psi, 1/psi, ln|psi| (true scale)
+// ------------------------------------------------------------------------------------------------
+struct PsiParams {
+  const double* Lenv; int ldL; int Dl;
+  const double* Renv; int ldR; int Dr;
+  const double* A; int ldA;
+  GroupSpec gs;
+  const int* cumeL; const int* cumeR;
+  double* psi; double* winv; double* lnpsi;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(NTHREADS) k_psi(PsiParams P) {
+  constexpr int MT = TM / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PanelSmem<TM>& sm = *reinterpret_cast<PanelSmem<TM>*>(smem_raw);
+  __shared__ const double* rowptr[TM];
+  __shared__ const double* rrow[TM];
+  __shared__ int rowid[TM];
+  __shared__ double rsum[TM][4];
+  int g, row0, nrows;
+  if (!locate_tile<TM>(P.gs, g, row0, nrows)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+  if (tid < TM) {
+    int id = -1;
+    if (tid < nrows) id = P.gs.perm ? P.gs.perm[row0 + tid] : row0 + tid;
+    rowid[tid] = id;
+    rowptr[tid] = id >= 0 ? P.Lenv + (long long)id * P.ldL : nullptr;
+    rrow[tid] = id >= 0 ? P.Renv + (long long)id * P.ldR : nullptr;
+  }
+  __syncthreads();
+  const double* B = P.A + (g / P.gs.gdiv) * P.gs.strideHi + (g % P.gs.gdiv) * P.gs.strideLo;
+  double part[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) part[i] = 0.0;
+  for (int col0 = 0; col0 < P.Dr; col0 += TN) {
+    double acc[MT][4][2];
+    panel_gemm<TM>(sm, rowptr, P.Dl, B, P.ldA, col0, P.Dr, acc);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      int r = wm * (TM / 2) + mt * 8 + (lane >> 2);
+      const double* rr = rrow[r];
+      if (!rr) continue;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        int col = col0 + wn * 32 + nt * 8 + 2 * (lane & 3);
+        if (col + 1 < P.Dr) {
+          double2 rv = *reinterpret_cast<const double2*>(rr + col);
+          part[mt] = fma(acc[mt][nt][0], rv.x, part[mt]);
+          part[mt] = fma(acc[mt][nt][1], rv.y, part[mt]);
+        } else if (col < P.Dr) {
+          part[mt] = fma(acc[mt][nt][0], rr[col], part[mt]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    double s = part[mt];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((lane & 3) == 0) rsum[wm * (TM / 2) + mt * 8 + (lane >> 2)][wn] = s;
+  }
+  __syncthreads();
+  if (tid < TM && rowid[tid] >= 0) {
+    int id = rowid[tid];
+    double psi = (rsum[tid][0] + rsum[tid][1]) + (rsum[tid][2] + rsum[tid][3]);
+    P.psi[id] = psi;
+    P.winv[id] = psi != 0.0 ? 1.0 / psi : 0.0;
+    P.lnpsi[id] = log(fabs(psi)) + (double)(P.cumeL[id] + P.cumeR[id]) * LN2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S[p,q] = sum_{n in group(p,q)} L_n (x) R_n / psi_n   — split over samples, partial tiles to a workspace
+// ------------------------------------------------------------------------------------------------
+constexpr int GT = 128;              // output tile is GT x GT
+constexpr int G_STRIDE = GT + 4;     // 132
+constexpr int GRAD_MAXCHUNK = 2048;  // samples per CTA (indices cached in shared memory)
+
+struct GradSmem {
+  double Ls[STAGES][KC][G_STRIDE];
+  double Rs[STAGES][KC][G_STRIDE];
+  double w[STAGES][KC];
+  int idx[GRAD_MAXCHUNK];
+};
+
+struct GradParams {
+  const double* Lenv; int ldL; int Dl;
+  const double* Renv; int ldR; int Dr;
+  const double* winv;
+  const int* perm; const int* goff; int ngroups; int d;
+  int kchunk;                      // samples per split, multiple of KC, <= GRAD_MAXCHUNK
+  double* ws; long long ws_stride; // partial slot stride in doubles
+  int ldA; int ldRpad;
+  int tiles_c;                     // number of column tiles
+};
+
+// grid = (max splits, tiles_a * tiles_c, ngroups)
+__global__ void __launch_bounds__(NTHREADS, 1) k_grad(GradParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GradSmem& sm = *reinterpret_cast<GradSmem*>(smem_raw);
+  const int g = blockIdx.z;
+  const int gbeg = P.goff[g], gend = P.goff[g + 1];
+  const int s0 = gbeg + blockIdx.x * P.kchunk;
+  if (s0 >= gend) return;
+  const int cnt = min(P.kchunk, gend - s0);
+  const int ta = blockIdx.y / P.tiles_c, tc = blockIdx.y % P.tiles_c;
+  const int a0 = ta * GT, c0 = tc * GT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+  for (int i = tid; i < cnt; i += NTHREADS) sm.idx[i] = P.perm ? P.perm[s0 + i] : s0 + i;
+  __syncthreads();
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nkc = (cnt + KC - 1) / KC;
+  auto load = [&](int stage, int kc) {
+    const int k0 = kc * KC;
+    for (int i = tid; i < KC * (GT / 2); i += NTHREADS) {
+      int kk = i / (GT / 2), c2 = i % (GT / 2);
+      int k = k0 + kk;
+      bool rv = k < cnt;
+      long long id = rv ? sm.idx[k] : 0;
+      int ca = a0 + c2 * 2, cc = c0 + c2 * 2;
+      int va = rv ? max(0, min(2, P.Dl - ca)) : 0;
+      int vc = rv ? max(0, min(2, P.Dr - cc)) : 0;
+      cp_async16(&sm.Ls[stage][kk][c2 * 2], va ? (const void*)(P.Lenv + id * P.ldL + ca) : (const void*)P.Lenv, va * 8);
+      cp_async16(&sm.Rs[stage][kk][c2 * 2], vc ? (const void*)(P.Renv + id * P.ldR + cc) : (const void*)P.Renv, vc * 8);
+    }
+    if (tid < KC) {
+      int k = k0 + tid;
+      bool rv = k < cnt;
+      cp_async8(&sm.w[stage][tid], rv ? (const void*)(P.winv + sm.idx[k]) : (const void*)P.winv, rv ? 8 : 0);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nkc) load(s, s);
+    cp_async_commit();
+  }
+  for (int kc = 0; kc < nkc; ++kc) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    int nx = kc + STAGES - 1;
+    if (nx < nkc) load(nx % STAGES, nx);
+    cp_async_commit();
+    const int st = kc % STAGES;
+#pragma unroll
+    for (int ks = 0; ks < KC; ks += 4) {
+      double a[8], b[4];
+      const double wv = sm.w[st][ks + (lane & 3)];
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) a[mt] = sm.Ls[st][ks + (lane & 3)][wm * 64 + mt * 8 + (lane >> 2)];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) b[nt] = sm.Rs[st][ks + (lane & 3)][wn * 32 + nt * 8 + (lane >> 2)] * wv;
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  }
+  cp_async_wait<0>();
+
+  const int p = g / P.d, q = g % P.d;
+  double* out = P.ws + (long long)blockIdx.x * P.ws_stride + (long long)p * P.Dl * P.ldA + (long long)q * P.ldRpad;
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt) {
+    int a = a0 + wm * 64 + mt * 8 + (lane >> 2);
+    if (a >= P.Dl) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      int c = c0 + wn * 32 + nt * 8 + 2 * (lane & 3);
+      double* o = out + (long long)a * P.ldA + c;
+      if (c + 1 < P.Dr) *reinterpret_cast<double2*>(o) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      else if (c < P.Dr) o[0] = acc[mt][nt][0];
+    }
+  }
+}
+
+// S[e] = sum over the splits of e's group, in split order (deterministic).  Pads are written as 0.
+__global__ void k_grad_reduce(const double* __restrict__ ws, long long ws_stride, const int* __restrict__ goff,
+                              int kchunk, int d, int Dl, int Dr, int ldA, int ldRpad, double* __restrict__ S) {
+  const long long total = (long long)d * Dl * ldA;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int row = (int)(e / ldA), col = (int)(e % ldA);
+    int p = row / Dl, q = col / ldRpad, c = col % ldRpad;
+    double s = 0.0;
+    if (c < Dr && q < d) {
+      int g = p * d + q;
+      int ng = goff[g + 1] - goff[g];
+      int ns = (ng + kchunk - 1) / kchunk;
+      for (int i = 0; i < ns; ++i) s += ws[(long long)i * ws_stride + e];
+    }
+    S[e] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler step (one site, all samples)
+// ------------------------------------------------------------------------------------------------
+struct SampleParams {
+  const double* Vin; int ldv; int Din;
+  double* Vout; int Dout;
+  const double* Bfirst; const double* Bsecond; int ldB;
+  const double* norm_in; const int* e_in;
+  double* norm_out; int* e_out;
+  const double* U;
+  uint8_t* pix_out;
+  int n; int strict; int pix_first; int both_norm;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(NTHREADS) k_sample_step(SampleParams P) {
+  constexpr int MT = TM / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PanelSmem<TM>& sm = *reinterpret_cast<PanelSmem<TM>*>(smem_raw);
+  __shared__ const double* rowptr[TM];
+  __shared__ int rowid[TM];
+  __shared__ double rscale[TM];
+  __shared__ double red[TM][4];
+  __shared__ double n1s[TM], m1s[TM], n2s[TM], m2s[TM];
+  __shared__ int accs[TM];
+  const int row0 = blockIdx.x * TM;
+  if (row0 >= P.n) return;
+  const int nrows = min(TM, P.n - row0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+  if (tid < TM) {
+    int id = tid < nrows ? row0 + tid : -1;
+    rowid[tid] = id;
+    rowptr[tid] = id >= 0 ? P.Vin + (long long)id * P.ldv : nullptr;
+    rscale[tid] = id >= 0 ? pow2d(-P.e_in[id]) : 0.0;
+    n1s[tid] = m1s[tid] = n2s[tid] = m2s[tid] = 0.0;
+    accs[tid] = 1;
+  }
+  __syncthreads();
+
+  // mode 0: first branch, store + norm; mode 1: second branch, norm only; mode 2: second branch, store rejected + norm
+  auto pass = [&](const double* B, int mode, double* nout, double* mout) {
+    double nn[MT], mm[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) nn[i] = mm[i] = 0.0;
+    for (int col0 = 0; col0 < P.Dout; col0 += TN) {
+      double acc[MT][4][2];
+      panel_gemm<TM>(sm, rowptr, P.Din, B, P.ldB, col0, P.Dout, acc);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        int r = wm * (TM / 2) + mt * 8 + (lane >> 2);
+        int id = rowid[r];
+        if (id < 0) continue;
+        double sc = rscale[r];
+        bool st = (mode == 0) || (mode == 2 && !accs[r]);
+        double* orow = P.Vout + (long long)id * P.ldv;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          int col = col0 + wn * 32 + nt * 8 + 2 * (lane & 3);
+          double v0 = acc[mt][nt][0] * sc, v1 = acc[mt][nt][1] * sc;
+          if (col + 1 < P.Dout) {
+            if (st) *reinterpret_cast<double2*>(orow + col) = make_double2(v0, v1);
+            nn[mt] = fma(v0, v0, nn[mt]); nn[mt] = fma(v1, v1, nn[mt]);
+            mm[mt] = fmax(mm[mt], fmax(fabs(v0), fabs(v1)));
+          } else if (col < P.Dout) {
+            if (st) orow[col] = v0;
+            nn[mt] = fma(v0, v0, nn[mt]);
+            mm[mt] = fmax(mm[mt], fabs(v0));
+          }
+        }
+      }
+    }
+    // norms
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      double s = nn[mt];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if ((lane & 3) == 0) red[wm * (TM / 2) + mt * 8 + (lane >> 2)][wn] = s;
+    }
+    __syncthreads();
+    if (tid < TM) nout[tid] = (red[tid][0] + red[tid][1]) + (red[tid][2] + red[tid][3]);
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      double m = mm[mt];
+      m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      if ((lane & 3) == 0) red[wm * (TM / 2) + mt * 8 + (lane >> 2)][wn] = m;
+    }
+    __syncthreads();
+    if (tid < TM) mout[tid] = fmax(fmax(red[tid][0], red[tid][1]), fmax(red[tid][2], red[tid][3]));
+    __syncthreads();
+  };
+
+  pass(P.Bfirst, 0, n1s, m1s);
+  if (P.both_norm) pass(P.Bsecond, 1, n2s, m2s);
+  int rej = 0;
+  if (tid < TM && rowid[tid] >= 0) {
+    int id = rowid[tid];
+    double sc = rscale[tid];
+    double den = P.both_norm ? (n1s[tid] + n2s[tid]) : (P.norm_in[id] * sc * sc);
+    double p = n1s[tid] / den;
+    double u = P.U[id];
+    int a = P.strict ? (u < p) : (u <= p);
+    accs[tid] = a;
+    rej = !a;
+  }
+  if (__syncthreads_or(rej)) pass(P.Bsecond, 2, n2s, m2s);
+  if (tid < TM && rowid[tid] >= 0) {
+    int id = rowid[tid];
+    int a = accs[tid];
+    P.norm_out[id] = a ? n1s[tid] : n2s[tid];
+    P.e_out[id] = frexp_exp(a ? m1s[tid] : m2s[tid]);
+    P.pix_out[id] = (uint8_t)(a ? P.pix_first : 1 - P.pix_first);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+// pixels [n][L] (levels, 255 unknown) -> phys [L][n] (d-1-level, 255 unknown)   (stater, TNutils.py:446-450)
+__global__ void k_embed(const uint8_t* __restrict__ pix, int n, int L, int d, uint8_t* __restrict__ phys) {
+  __shared__ uint8_t tile[32][33];
+  int s0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int nn = n0 + j, s = s0 + threadIdx.x;
+    uint8_t v = 255;
+    if (nn < n && s < L) { uint8_t x = pix[(long long)nn * L + s]; v = x < d ? (uint8_t)(d - 1 - x) : 255; }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int s = s0 + j, nn = n0 + threadIdx.x;
+    if (s < L && nn < n) phys[(long long)s * n + nn] = tile[threadIdx.x][j];
+  }
+}
+
+// inverse: phys [L][n] -> pixels [n][L]
+__global__ void k_unembed(const uint8_t* __restrict__ phys, int n, int L, int d, uint8_t* __restrict__ pix) {
+  __shared__ uint8_t tile[32][33];
+  int s0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int s = s0 + j, nn = n0 + threadIdx.x;
+    tile[j][threadIdx.x] = (s < L && nn < n) ? phys[(long long)s * n + nn] : 255;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int nn = n0 + j, s = s0 + threadIdx.x;
+    if (nn < n && s < L) pix[(long long)nn * L + s] = tile[threadIdx.x][j];
+  }
+}
+
+// Stable counting sort of sample ids by key.  One CTA (256 threads) per problem (blockIdx.x):
+//   pair mode  (col1 != nullptr): key = col0[i]*d + col1[i]  with col = phys + (b or b+1)*n
+//   single mode:                  key = col0[i]
+// `subset` (optional) restricts to the listed sample ids (minibatch); then m = subset size.
+// Samples whose key is out of range (unknown pixels) are dropped.
+__global__ void __launch_bounds__(256) k_build_perm(const uint8_t* __restrict__ phys, int n, int d, int pair,
+                                                    const int* __restrict__ subset, int m,
+                                                    int* __restrict__ perm, int* __restrict__ goff, int perm_stride) {
+  constexpr int T = 256;
+  constexpr int GMAX = 16;   // d <= 4
+  __shared__ int cnt[GMAX][T + 1];
+  __shared__ int gtot[GMAX + 1];
+  const int b = blockIdx.x;
+  const int G = pair ? d * d : d;
+  const uint8_t* c0 = phys + (long long)b * n;
+  const uint8_t* c1 = c0 + n;
+  int* out = perm + (long long)b * perm_stride;
+  int* go = goff + (long long)b * (G + 1);
+  const int t = threadIdx.x;
+  const int len = (m + T - 1) / T;
+  const int beg = min(m, t * len), end = min(m, beg + len);
+  for (int g = 0; g < G; ++g) cnt[g][t] = 0;
+  for (int i = beg; i < end; ++i) {
+    int id = subset ? subset[i] : i;
+    int x = c0[id], y = pair ? c1[id] : 0;
+    if (x < d && y < d) cnt[pair ? x * d + y : x][t]++;
+  }
+  __syncthreads();
+  // exclusive scan over (g major, t minor): one warp per group computes the within-group scan
+  for (int g = t >> 5; g < G; g += T / 32) {
+    int lane = t & 31, run = 0;
+    for (int base = 0; base < T; base += 32) {
+      int v = cnt[g][base + lane], x = v;
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      cnt[g][base + lane] = run + x - v;
+      run += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) cnt[g][T] = run;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int g = 0; g < G; ++g) { gtot[g] = run; go[g] = run; run += cnt[g][T]; }
+    gtot[G] = run; go[G] = run;
+  }
+  __syncthreads();
+  for (int i = beg; i < end; ++i) {
+    int id = subset ? subset[i] : i;
+    int x = c0[id], y = pair ? c1[id] : 0;
+    if (x < d && y < d) {
+      int g = pair ? x * d + y : x;
+      out[gtot[g] + cnt[g][t]++] = id;
+    }
+  }
+}
+
+// partial sums of squares over the valid region of an engine-layout matrix; part[blockIdx.x]
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  __syncthreads();
+  return r;   // valid in thread 0
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = -INFINITY;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmax(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+
+constexpr int RED_BLOCKS = 64;
+
+__global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ A, int rows, int ldA, int Dr, int ldRpad,
+                                               double* __restrict__ part) {
+  __shared__ double sh[8];
+  const long long total = (long long)rows * ldA;
+  double s = 0.0;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int c = (int)(e % ldA) % ldRpad;
+    if (c < Dr) { double v = A[e]; s = fma(v, v, s); }
+  }
+  double r = block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+
+// A2 = A - lr * (A/Z - S/batch + mom);  partials: [0] max(A2) (signed), [1] sum A2^2, [2] sum dNLL, [3] nonfinite count
+__global__ void __launch_bounds__(256) k_update(const double* __restrict__ A, const double* __restrict__ S,
+                                                const double* __restrict__ partZ, int rows, int ldA, int Dr, int ldRpad,
+                                                double batch, double lr, double mom, double* __restrict__ A2,
+                                                double* __restrict__ part2, double* __restrict__ scal) {
+  __shared__ double sh[8];
+  __shared__ double Zs;
+  if (threadIdx.x == 0) { double z = 0.0; for (int i = 0; i < RED_BLOCKS; ++i) z += partZ[i]; Zs = z; if (blockIdx.x == 0) scal[0] = z; }
+  __syncthreads();
+  const double Z = Zs;
+  const long long total = (long long)rows * ldA;
+  double mx = -INFINITY, ss = 0.0, sd = 0.0, nf = 0.0;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int c = (int)(e % ldA) % ldRpad;
+    double out = 0.0;
+    if (c < Dr) {
+      double a = A[e];
+      double dn = a / Z - S[e] / batch;
+      out = a - lr * (dn + mom);
+      mx = fmax(mx, out); ss = fma(out, out, ss); sd += dn;
+      if (!isfinite(out)) nf += 1.0;
+    }
+    A2[e] = out;
+  }
+  double r0 = block_max(mx, sh), r1 = block_sum(ss, sh), r2 = block_sum(sd, sh), r3 = block_sum(nf, sh);
+  if (threadIdx.x == 0) {
+    part2[blockIdx.x * 4 + 0] = r0; part2[blockIdx.x * 4 + 1] = r1;
+    part2[blockIdx.x * 4 + 2] = r2; part2[blockIdx.x * 4 + 3] = r3;
+  }
+}
+
+// W (column-major, rows x (d*Dr), compact) = A2 / c, c = max(A2) or sqrt(sum A2^2).  scal[4]=mean dNLL, [5]=c, [7]=nonfinite
+__global__ void __launch_bounds__(256) k_scale_to_colmajor(const double* __restrict__ A2, const double* __restrict__ part2,
+                                                           int rows, int ldA, int d, int Dr, int ldRpad, int renorm,
+                                                           double* __restrict__ W, double* __restrict__ scal) {
+  __shared__ double cs;
+  if (threadIdx.x == 0) {
+    double mx = -INFINITY, ss = 0.0, sd = 0.0, nf = 0.0;
+    for (int i = 0; i < RED_BLOCKS; ++i) { mx = fmax(mx, part2[i * 4]); ss += part2[i * 4 + 1]; sd += part2[i * 4 + 2]; nf += part2[i * 4 + 3]; }
+    double c = renorm == 0 ? mx : sqrt(ss);
+    cs = c;
+    if (blockIdx.x == 0) { scal[4] = sd / ((double)rows * d * Dr); scal[5] = c; scal[7] = nf; }
+  }
+  __syncthreads();
+  const double c = cs;
+  const int ncols = d * Dr;
+  const long long total = (long long)rows * ncols;
+  // consecutive threads walk consecutive rows of W (coalesced writes); reads are strided but L2-resident
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int cc = (int)(e / rows), r = (int)(e % rows);
+    int q = cc / Dr, cidx = cc % Dr;
+    W[e] = A2[(long long)r * ldA + q * ldRpad + cidx] / c;
+  }
+}
+
+// chi from the singular values (quimb split rule, oracle/born_oracle.py::split); iscal: [0]=chi, [1]=info copy
+__global__ void k_chi(const double* __restrict__ s, int r, double cutoff, int max_bond, const int* __restrict__ info,
+                      int* __restrict__ iscal, double* __restrict__ scal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int chi;
+  if (cutoff > 0.0) {
+    chi = 0;
+    double thr = cutoff * s[0];
+    for (int i = 0; i < r; ++i) if (s[i] > thr) ++chi;
+    if (chi < 1) chi = 1;
+    if (max_bond > 0 && chi > max_bond) chi = max_bond;
+  } else if (max_bond > 0) chi = min(max_bond, r);
+  else chi = r;
+  double t = 0.0;
+  for (int i = chi; i < r; ++i) t = fma(s[i], s[i], t);
+  iscal[0] = chi; iscal[1] = info ? info[0] : 0;
+  scal[3] = (double)chi; scal[6] = sqrt(t);
+}
+
+// Deterministic gauge: sgn[b] = sign(sum_i w_i U[i,b]), w_i = 1 + frac(phi*(i_ref+1)), i_ref = a*d + p the row
+// index in the reference ordering (oracle/born_oracle.py::gauge_signs).  One warp per column.
+__global__ void __launch_bounds__(256) k_gauge_signs(const double* __restrict__ U, int mA, int d, int Dl,
+                                                     const int* __restrict__ iscal, double* __restrict__ sgn) {
+  const int chi = iscal[0];
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < chi; b += gridDim.x * 8) {
+    double s = 0.0;
+    for (int r = lane; r < mA; r += 32) {
+      int p = r / Dl, a = r % Dl;
+      double x = 0.6180339887498949 * (double)(a * d + p + 1);
+      s = fma(1.0 + (x - floor(x)), U[(long long)b * mA + r], s);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sgn[b] = s < 0.0 ? -1.0 : 1.0;
+  }
+}
+
+// Write both storage forms of the two new site tensors from the SVD factors.
+//   U: column-major (mA x r), mA = d*Dl, U[b*mA + p*Dl + a];  V: column-major (nA x r), V[b*nA + q*Dr + c]
+//   site k   : L-form [a][p][b] ld = ldx, R-form [b][p][a] ld = ldl;   (times s_b when absorbing left)
+//   site k+1 : L-form [b][q][c] ld = ldr, R-form [c][q][b] ld = ldx;   (times s_b when absorbing right)
+__global__ void __launch_bounds__(256) k_factor_out(const double* __restrict__ U, const double* __restrict__ V,
+                                                    const double* __restrict__ s, const double* __restrict__ sgn,
+                                                    const int* __restrict__ iscal,
+                                                    int d, int Dl, int Dr, int going_right,
+                                                    double* __restrict__ Lk, double* __restrict__ Rk,
+                                                    double* __restrict__ Lk1, double* __restrict__ Rk1) {
+  const int chi = iscal[0];
+  const int ldx = (chi + 1) & ~1, ldl = (Dl + 1) & ~1, ldr = (Dr + 1) & ~1;
+  const int mA = d * Dl, nA = d * Dr;
+  const long long nU = (long long)chi * mA, nV = (long long)chi * nA;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < nU + nV; e += 256LL * gridDim.x) {
+    if (e < nU) {
+      int b = (int)(e / mA), pa = (int)(e % mA), p = pa / Dl, a = pa % Dl;
+      double v = U[e] * sgn[b];
+      if (!going_right) v *= s[b];
+      Rk[((long long)b * d + p) * ldl + a] = v;
+      Lk[((long long)a * d + p) * ldx + b] = v;
+    } else {
+      long long f = e - nU;
+      int b = (int)(f / nA), qc = (int)(f % nA), q = qc / Dr, c = qc % Dr;
+      double v = V[f] * sgn[b];
+      if (going_right) v *= s[b];
+      Lk1[((long long)b * d + q) * ldr + c] = v;
+      Rk1[((long long)c * d + q) * ldx + b] = v;
+    }
+  }
+}
+
+// reference layout (Dl,Dr,d) row-major  <->  the two storage forms
+__global__ void k_site_from_ref(const double* __restrict__ ref, int d, int Dl, int Dr, double* __restrict__ Lf, double* __restrict__ Rf) {
+  const int ldl = (Dl + 1) & ~1, ldr = (Dr + 1) & ~1;
+  const long long total = (long long)Dl * Dr * d;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int p = (int)(e % d), b = (int)((e / d) % Dr), a = (int)(e / ((long long)d * Dr));
+    double v = ref[e];
+    Lf[((long long)a * d + p) * ldr + b] = v;
+    Rf[((long long)b * d + p) * ldl + a] = v;
+  }
+}
+__global__ void k_site_to_ref(const double* __restrict__ Lf, int d, int Dl, int Dr, double* __restrict__ ref) {
+  const int ldr = (Dr + 1) & ~1;
+  const long long total = (long long)Dl * Dr * d;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int p = (int)(e % d), b = (int)((e / d) % Dr), a = (int)(e / ((long long)d * Dr));
+    ref[e] = Lf[((long long)a * d + p) * ldr + b];
+  }
+}
+// engine layout rows (p,a) x cols (q,c) ld=ldA  <->  reference (Dl,d,Dr,d) row-major
+__global__ void k_engine_to_ref(const double* __restrict__ E, int d, int Dl, int Dr, int ldA, int ldRpad, double* __restrict__ ref) {
+  const long long total = (long long)Dl * d * Dr * d;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int q = (int)(e % d), c = (int)((e / d) % Dr), p = (int)((e / ((long long)d * Dr)) % d), a = (int)(e / ((long long)d * Dr * d));
+    ref[e] = E[((long long)p * Dl + a) * ldA + q * ldRpad + c];
+  }
+}
+__global__ void k_ref_to_engine(const double* __restrict__ ref, int d, int Dl, int Dr, int ldA, int ldRpad, double* __restrict__ E) {
+  const long long total = (long long)Dl * d * Dr * d;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int q = (int)(e % d), c = (int)((e / d) % Dr), p = (int)((e / ((long long)d * Dr)) % d), a = (int)(e / ((long long)d * Dr * d));
+    E[((long long)p * Dl + a) * ldA + q * ldRpad + c] = ref[e];
+  }
+}
+
+// sum_{i<m} lnpsi[ids[i]] (finite terms) and the number of zero psi, appended after the gradient (tail[0], tail[1])
+__global__ void __launch_bounds__(1024) k_lnpsi_reduce(const double* __restrict__ lnpsi, const double* __restrict__ psi,
+                                                       const int* __restrict__ ids, int m, double* __restrict__ tail) {
+  __shared__ double sh[32];
+  double s = 0.0, z = 0.0;
+  // fixed assignment of elements to threads + fixed-order tree => deterministic
+  for (int i = threadIdx.x; i < m; i += 1024) {
+    int id = ids ? ids[i] : i;
+    if (psi[id] == 0.0) z += 1.0; else s += lnpsi[id];
+  }
+  double r0 = block_sum(s, sh), r1 = block_sum(z, sh);
+  if (threadIdx.x == 0) { tail[0] = r0; tail[1] = r1; }
+}
+
+// boundary rows: E[n][0] = 1, e = 1 (1 = 0.5 * 2^1), cume = 0
+__global__ void k_init_boundary(double* __restrict__ E, int ld, int n, int* __restrict__ e, int* __restrict__ cume) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { E[(long long)i * ld] = 1.0; e[i] = 1; cume[i] = 0; }
+}
+
+// rows divided by their max-abs (what the reference stores, TNutils.py:464-465) into a compact n x D buffer
+__global__ void k_env_export(const double* __restrict__ E, int ld, int D, int n, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* r = E + (long long)i * ld;
+  double m = 0.0;
+  for (int j = 0; j < D; ++j) m = fmax(m, fabs(r[j]));
+  for (int j = 0; j < D; ++j) out[(long long)i * D + j] = r[j] / m;
+}
+
+__global__ void k_rownorm2(const double* __restrict__ E, int ld, int D, int n, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* r = E + (long long)i * ld;
+  double s = 0.0;
+  for (int j = 0; j < D; ++j) s = fma(r[j], r[j], s);
+  out[i] = s;
+}
+
+// final scalar of a full left chain: ln|v| + cume*ln2, sign
+__global__ void k_finish_logpsi(const double* __restrict__ E, int ld, const int* __restrict__ cume, int n,
+                                double* __restrict__ lnabs, double* __restrict__ sign) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = E[(long long)i * ld];
+  lnabs[i] = log(fabs(v)) + (double)cume[i] * LN2;
+  sign[i] = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
+}
+
+// counter-based uniforms in [0,1): splitmix64(seed, site, sample) >> 11 * 2^-53
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__global__ void k_fill_uniform(double* __restrict__ U, int n, uint64_t seed, int site) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint64_t h = splitmix64(splitmix64(seed ^ (0xD1B54A32D192ED03ULL * (uint64_t)(site + 1))) + (uint64_t)i);
+    U[i] = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+  }
+}
+
+__global__ void k_copy_u8_rows(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long count) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = src[i];
+}
+__global__ void k_phys_to_pix(uint8_t* __restrict__ p, long long count, int d) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < count) { uint8_t x = p[i]; p[i] = x < d ? (uint8_t)(d - 1 - x) : 255; }
+}
+
+}  // namespace bm

@@ -1,0 +1,298 @@
+"""BornEngine — Python host wrapper over libbm.so (include/bm.h).
+
+One engine per process/GPU.  All arithmetic of the hot path runs in the CUDA library; PyTorch is used for
+the gradient buffer (so that torch.distributed can all-reduce it over NCCL) and for stream plumbing.
+Reference functions replaced (TNutils.py): left_right_cache :457, sequential_update :504,
+learning_step_cached :1510, learning_epoch_cached :1570, computeNLL :872, generate_samples :1829,
+generate_sample :1874 / reconstruct :2053 (known-prefix case).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import RENORM, RULE, SVD, ZeroPsiError, check, lib
+
+SCALAR_NAMES = ('Z', 'sum_logpsi', 'n_zero_psi', 'chi', 'mean_dnll', 'renorm_div', 'trunc_err', 'nonfinite')
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def sweep_schedule(L):
+    """[0..L-2] + [L-2..0]  (TNutils.py:1597)."""
+    return list(range(0, L - 1)) + list(range(L - 2, -1, -1))
+
+
+class BornEngine:
+    def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gesvdj', dist_group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('BornEngine needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.L, self.d, self.Dcap = int(n_sites), int(phys_dim), int(max_bond)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        torch.cuda.set_device(self.device)
+        self._lib = lib()
+        self._ctx = C.c_void_p()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        code = self._lib.bm_create(C.byref(self._ctx), self.device, self.L, self.d, self.Dcap, C.c_void_p(stream))
+        check(self._ctx, code)
+        check(self._ctx, self._lib.bm_set_svd(self._ctx, SVD[svd]))
+        ld = (self.Dcap + 1) & ~1
+        self._S = torch.zeros(self.d * self.Dcap * self.d * ld + 2, dtype=torch.float64, device=f'cuda:{self.device}')
+        self.N = 0
+        self.N_total = 0
+        self.group = dist_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(dist_group)
+
+    def close(self):
+        if getattr(self, '_ctx', None) is not None and self._ctx.value:
+            self._lib.bm_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data / model ----------------------------------------------------------------------------
+    def set_data(self, imgs, n_total=None):
+        """imgs: (N,L) pixel levels 0..d-1 of THIS rank's shard.  n_total: global sample count."""
+        a = np.ascontiguousarray(np.asarray(imgs), dtype=np.int64)
+        if a.ndim != 2 or a.shape[1] != self.L:
+            raise ValueError(f'expected (N,{self.L}) images')
+        if a.min() < 0 or a.max() >= self.d:
+            raise ValueError('training images must hold levels 0..d-1 (no unknown pixels)')
+        px = np.ascontiguousarray(a.astype(np.uint8))
+        check(self._ctx, self._lib.bm_set_data(self._ctx, _ptr(px), px.shape[0]))
+        self.N = px.shape[0]
+        self.N_total = int(n_total) if n_total is not None else self.N * self.world
+
+    def set_site(self, k, t):
+        t = np.asarray(t, dtype=np.float64)
+        if t.ndim == 2:
+            t = t.reshape(1, t.shape[0], t.shape[1]) if k == 0 else t.reshape(t.shape[0], 1, t.shape[1])
+        t = np.ascontiguousarray(t)
+        if t.shape[2] != self.d:
+            raise ValueError('physical dimension mismatch')
+        check(self._ctx, self._lib.bm_set_site(self._ctx, k, _ptr(t), t.shape[0], t.shape[1]))
+
+    def set_mps(self, mps):
+        if len(mps) != self.L:
+            raise ValueError('wrong number of sites')
+        for k, t in enumerate(mps):
+            self.set_site(k, t)
+
+    def site_dims(self, k):
+        dl, dr = C.c_int(), C.c_int()
+        check(self._ctx, self._lib.bm_site_dims(self._ctx, k, C.byref(dl), C.byref(dr)))
+        return dl.value, dr.value
+
+    def get_site(self, k, squeeze=True):
+        dl, dr = self.site_dims(k)
+        out = np.empty((dl, dr, self.d))
+        check(self._ctx, self._lib.bm_get_site(self._ctx, k, _ptr(out), None, None))
+        if squeeze and k == 0:
+            return out[0]
+        if squeeze and k == self.L - 1:
+            return out[:, 0, :]
+        return out
+
+    def get_mps(self):
+        return [self.get_site(k) for k in range(self.L)]
+
+    def bond_sizes(self):
+        return [self.site_dims(k)[1] for k in range(self.L - 1)]
+
+    # ---- environments ----------------------------------------------------------------------------
+    def env_build(self, k=0):
+        check(self._ctx, self._lib.bm_env_build(self._ctx, k))
+
+    def env_advance(self, k, going_right):
+        check(self._ctx, self._lib.bm_env_advance(self._ctx, k, 1 if going_right else 0))
+
+    def env_get(self, side, j):
+        D = self.site_dims(j)[0] if 0 < j < self.L else 1
+        out = np.empty((self.N, D))
+        got = C.c_int()
+        check(self._ctx, self._lib.bm_env_get(self._ctx, side, j, _ptr(out), C.byref(got)))
+        assert got.value == D
+        return out
+
+    # ---- two-site step ---------------------------------------------------------------------------
+    def grad_dims(self, k):
+        v = [C.c_int() for _ in range(5)]
+        check(self._ctx, self._lib.bm_grad_dims(self._ctx, k, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)   # rows, ld, Dl, Dr, ldR
+
+    def step_grad(self, k, mask=None):
+        """merge + psi + S = sum psi'/psi on this rank's samples; returns the device buffer view
+        (rows*ld + 2 doubles: S, sum ln|psi|, n_zero)."""
+        if mask is not None:
+            m = np.ascontiguousarray(np.asarray(mask), dtype=np.int32)
+            code = self._lib.bm_step_grad(self._ctx, k, _ptr(m), m.size, C.c_void_p(self._S.data_ptr()))
+        else:
+            code = self._lib.bm_step_grad(self._ctx, k, None, 0, C.c_void_p(self._S.data_ptr()))
+        check(self._ctx, code)
+        rows, ld = self.grad_dims(k)[:2]
+        return self._S[:rows * ld + 2]
+
+    def step_update(self, k, S, batch_total, lr, going_right=True, renorm='max', max_bond=None, cutoff=1e-10,
+                    mom_bias=0.0, want_s=False):
+        rows, ld, Dl, Dr, _ = self.grad_dims(k)
+        scal = np.zeros(8)
+        s = np.empty(min(rows, self.d * Dr)) if want_s else None
+        code = self._lib.bm_step_update(self._ctx, k, C.c_void_p(S.data_ptr()), float(batch_total), float(lr),
+                                        RENORM[renorm], 1 if going_right else 0,
+                                        int(max_bond) if max_bond else 0, float(cutoff), float(mom_bias),
+                                        _ptr(scal), _ptr(s) if want_s else None)
+        out = dict(zip(SCALAR_NAMES, scal))
+        out['chi'] = int(out['chi'])
+        if want_s:
+            out['s_all'] = s
+            out['s'] = s[:out['chi']]
+        try:
+            check(self._ctx, code)
+        except ZeroPsiError:
+            out['skipped'] = True
+            return out
+        out['skipped'] = False
+        return out
+
+    def step(self, k, lr, going_right=True, renorm='max', max_bond=None, cutoff=1e-10, mask=None, mom_bias=0.0,
+             want_s=False, batch_total=None, advance=True):
+        """One learning_step_cached + write-back + sequential_update (TNutils.py:1603-1620)."""
+        S = self.step_grad(k, mask)
+        if self.world > 1:
+            torch.distributed.all_reduce(S, group=self.group)   # sum over sample shards (NCCL over NVLink)
+        if batch_total is None:
+            batch_total = self.N_total if mask is None else len(mask) * self.world
+        out = self.step_update(k, S, batch_total, lr, going_right, renorm, max_bond, cutoff, mom_bias, want_s)
+        if advance:
+            self.env_advance(k, going_right)
+        out['nll_batch'] = -2.0 * out['sum_logpsi'] / batch_total + math.log(out['Z']) if out['Z'] > 0 else float('nan')
+        return out
+
+    def learning_step_host(self, k, site_k, site_k1, lr, going_right=True, **kw):
+        """Reference-style call with HOST tensors in and out (learning_step_cached + write-back +
+        sequential_update, TNutils.py:1603-1620): uploads the two site tensors, runs the step on the
+        device-resident environments, downloads the two new site tensors."""
+        self.set_site(k, site_k)
+        self.set_site(k + 1, site_k1)
+        out = self.step(k, lr, going_right, **kw)
+        return self.get_site(k), self.get_site(k + 1), out
+
+    def get_merged(self):
+        """merged tensor A of the last step_grad, reference index order (Dl,d,Dr,d) (TNutils.py:1388)."""
+        raise RuntimeError('use get_merged_at(k) right after step_grad(k)')
+
+    def get_merged_at(self, k):
+        rows, ld, Dl, Dr, _ = self.grad_dims(k)
+        out = np.empty((Dl, self.d, Dr, self.d))
+        check(self._ctx, self._lib.bm_get_merged(self._ctx, _ptr(out)))
+        return out
+
+    def grad_to_ref(self, k, S):
+        """engine-layout device buffer -> (Dl,d,Dr,d) numpy array."""
+        rows, ld, Dl, Dr, _ = self.grad_dims(k)
+        out = np.empty((Dl, self.d, Dr, self.d))
+        check(self._ctx, self._lib.bm_engine_to_ref(self._ctx, k, C.c_void_p(S.data_ptr()), _ptr(out)))
+        return out
+
+    def epoch(self, lr, renorm='max', max_bond=None, cutoff=1e-10, batch_size=None, rng=None, callback=None):
+        """One reference epoch: 2(L-1) steps over the schedule, centre ends at site 0 (TNutils.py:1592-1625)."""
+        L = self.L
+        going_right = True
+        outs = []
+        for k in sweep_schedule(L):
+            mask = None
+            if batch_size is not None and batch_size < self.N:
+                guide = (rng if rng is not None else np.random).permutation(self.N)
+                mask = guide[:batch_size]
+            o = self.step(k, lr, going_right, renorm, max_bond, cutoff, mask)
+            if callback is not None:
+                callback(k, going_right, o)
+            outs.append(o)
+            if k == L - 2:
+                going_right = False
+        return outs
+
+    # ---- likelihood ------------------------------------------------------------------------------
+    def logpsi(self, imgs):
+        a = np.ascontiguousarray(np.asarray(imgs), dtype=np.int64)
+        px = np.where(a < 0, 255, a).astype(np.uint8)
+        px = np.ascontiguousarray(px)
+        ln = np.empty(px.shape[0]); sg = np.empty(px.shape[0])
+        check(self._ctx, self._lib.bm_logpsi(self._ctx, _ptr(px), px.shape[0], _ptr(ln), _ptr(sg)))
+        return sg, ln
+
+    def last_logpsi(self):
+        out = np.empty(self.N)
+        check(self._ctx, self._lib.bm_last_logpsi(self._ctx, _ptr(out)))
+        return out
+
+    def norm2_centre(self, k=0):
+        t = self.get_site(k)
+        return float(np.sum(t * t))
+
+    def nll(self, imgs, centre=0):
+        """computeNLL(mps, imgs, canonicalized_index) (TNutils.py:872-890)."""
+        _, ln = self.logpsi(imgs)
+        return float(-2.0 * ln.sum() / len(ln) + math.log(self.norm2_centre(centre)))
+
+    # ---- sampling --------------------------------------------------------------------------------
+    def sample(self, n, U=None, seed=0, rule='batched', prefix=None, start_site=0):
+        """generate_samples (rule='batched', TNutils.py:1829) or the generate_sample/reconstruct rule
+        (rule='single', :1874) for n samples in lock step.  U: (L-start_site, n) uniforms, site-major."""
+        out = np.empty((n, self.L), dtype=np.uint8)
+        up = None
+        if U is not None:
+            U = np.ascontiguousarray(np.asarray(U, dtype=np.float64))
+            if U.shape != (self.L - start_site, n):
+                raise ValueError(f'U must have shape ({self.L - start_site},{n})')
+            up = _ptr(U)
+        pp = None
+        if prefix is not None:
+            a = np.asarray(prefix)
+            px = np.ascontiguousarray(np.where(a < 0, 255, a).astype(np.uint8))
+            if px.shape != (n, self.L):
+                raise ValueError('prefix images must be (n,L)')
+            pp = _ptr(px)
+        check(self._ctx, self._lib.bm_sample(self._ctx, n, RULE[rule], start_site, up, C.c_uint64(seed), pp, _ptr(out)))
+        return out
+
+    def sample_device_ms(self, n, seed=0, rule='batched'):
+        ms = C.c_float()
+        check(self._ctx, self._lib.bm_sample_device(self._ctx, n, RULE[rule], C.c_uint64(seed), C.byref(ms)))
+        return ms.value
+
+    TIMING_SLOTS = ('env_advance', 'psi', 'grad', 'grad_reduce', 'merge', 'svd', 'unused', 'sample_step')
+
+    def set_timing(self, on):
+        check(self._ctx, self._lib.bm_set_timing(self._ctx, 1 if on else 0))
+
+    def get_timing(self):
+        ms = (C.c_double * 8)(); n = (C.c_longlong * 8)()
+        check(self._ctx, self._lib.bm_get_timing(self._ctx, ms, n))
+        return {name: (ms[i], n[i]) for i, name in enumerate(self.TIMING_SLOTS)}
+
+    def launch_count(self):
+        return int(self._lib.bm_launch_count(self._ctx))
+
+
+def uniforms_reference(seed, site, n):
+    """Host mirror of the device generator k_fill_uniform (splitmix64 counter hash)."""
+    M = (1 << 64) - 1
+
+    def sm(x):
+        x = (x + 0x9E3779B97F4A7C15) & M
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
+        return x ^ (x >> 31)
+    base = sm(seed ^ ((0xD1B54A32D192ED03 * (site + 1)) & M))
+    return np.array([(sm((base + i) & M) >> 11) / 9007199254740992.0 for i in range(n)])

@@ -146,7 +146,7 @@ def random_mps(L, bond_dim, d=2, rng=None, normalize=True):
     for k in range(L):
         dl = 1 if k == 0 else bond_dim
         dr = 1 if k == L - 1 else bond_dim
-        mats.append(rng.standard_normal((dl, dr, d)))
+        mats.append(rng.standard_normal((dl, dr, d)) / np.sqrt(dr * d))
     mps = from_site3(mats)
     if normalize:
         mps = normalize_mps(mps)
@@ -193,27 +193,29 @@ def left_canonize(mps):
     return canonize(mps, len(mps) - 1)
 
 
-def norm2_full(mps):
-    """<mps|mps> by transfer-matrix contraction (the reference's `mps @ mps`, TNutils.py:884)."""
+def lognorm2(mps):
+    """ln <mps|mps> by transfer-matrix contraction with per-site rescaling (safe for long chains)."""
     e = np.ones((1, 1))
+    ls = 0.0
     for k in range(len(mps)):
         m = site3(mps, k)
-        e = np.einsum('ab,acp,bdp->cd', e, m, m)
-    return float(e[0, 0])
+        e = sum(m[:, :, p].T @ e @ m[:, :, p] for p in range(m.shape[2]))
+        mx = np.abs(e).max()
+        e = e / mx
+        ls += np.log(mx)
+    return float(np.log(e[0, 0]) + ls)
+
+
+def norm2_full(mps):
+    """<mps|mps> (the reference's `mps @ mps`, TNutils.py:884)."""
+    return float(np.exp(lognorm2(mps)))
 
 
 def normalize_mps(mps):
-    """quimb `normalize()` (TNutils.py:2000,2057): divide so that <mps|mps> = 1 (the factor is
-    spread over one site; only the global scale matters for every quantity we compare)."""
-    out = [t.copy() for t in mps]
-    # distribute the scale to avoid under/overflow for long chains
-    L = len(out)
-    for k in range(L):
-        nk = np.linalg.norm(out[k])
-        out[k] = out[k] / nk
-    n2 = norm2_full(out)
-    out[0] = out[0] / np.sqrt(n2)
-    return out
+    """quimb `normalize()` (TNutils.py:2000,2057): <mps|mps> = 1.  The factor is spread evenly over the
+    sites (only the global scale matters for every quantity we compare)."""
+    f = np.exp(-lognorm2(mps) / (2 * len(mps)))
+    return [t * f for t in mps]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -394,7 +396,19 @@ def psi_and_grad_literal(A, lv, rv, pk, pk1):
     return psi, S
 
 
-def split(A, absorb, max_bond=None, cutoff=1e-10):
+def gauge_signs(U):
+    """Deterministic sign convention for singular vectors used by the CUDA engine (k_gauge_signs):
+    column b is flipped so that sum_i w_i U[i,b] > 0 with the fixed weights w_i = 1 + frac(phi*(i+1)).
+    The reference keeps whatever LAPACK returns; its `A/A.data.max()` step (TNutils.py:1542) makes the
+    trajectory depend on these signs, so trajectory-level parity needs both sides in one gauge."""
+    i = np.arange(1, U.shape[0] + 1, dtype=np.float64)
+    w = 1.0 + np.modf(0.6180339887498949 * i)[0]
+    sg = np.sign(w @ U)
+    sg[sg == 0] = 1.0
+    return sg
+
+
+def split(A, absorb, max_bond=None, cutoff=1e-10, gauge=None):
     """quimb 1.3.0 `Tensor.split(left_inds=[i{k-1},v{k}], absorb=..., max_bond=, cutoff=)` with its
     defaults method='svd', cutoff_mode='rel', renorm=None (call sites TNutils.py:1434-1441,
     :1557-1564).  UNPINNED restatement (quimb is not vendored):
@@ -414,6 +428,9 @@ def split(A, absorb, max_bond=None, cutoff=1e-10):
     else:
         chi = s.size
     U, sk, Vh = U[:, :chi], s[:chi], Vh[:chi]
+    if gauge == 'fixed':
+        sg = gauge_signs(U)
+        U, Vh = U * sg[None, :], Vh * sg[:, None]
     if absorb == 'right':
         Vh = sk[:, None] * Vh
     elif absorb == 'left':
@@ -433,7 +450,7 @@ def write_back(mps, k, left, right):
 
 
 def two_site_step(mps, k, lv, rv, pk, pk1, lr, going_right=True, renorm='max',
-                  max_bond=None, cutoff=1e-10, update_wrap=None, batch=None):
+                  max_bond=None, cutoff=1e-10, update_wrap=None, batch=None, gauge=None):
     """One `learning_step_cached` (TNutils.py:1510-1568) / `learning_step` (:1380-1445).
     lv, rv: environments of the (mini)batch; returns dict with the new factors and diagnostics.
     renorm='max' is :1542 (signed max), 'l2' is :1419."""
@@ -450,7 +467,7 @@ def two_site_step(mps, k, lv, rv, pk, pk1, lr, going_right=True, renorm='max',
         A2 = A2 / np.sqrt(np.sum(A2 * A2))
     else:
         raise ValueError(renorm)
-    left, right, sk, s_all = split(A2, 'right' if going_right else 'left', max_bond, cutoff)
+    left, right, sk, s_all = split(A2, 'right' if going_right else 'left', max_bond, cutoff, gauge)
     return dict(A=A, Z=Z, psi=psi, S=S, dNLL=dNLL, A_new=A2, left=left, right=right, s=sk, s_all=s_all)
 
 
@@ -461,7 +478,7 @@ def sweep_schedule(L):
 
 def learning_epoch_cached(mps, imgs, epochs, lr, cache=None, batch_size=None, renorm='max',
                           max_bond=None, cutoff=1e-10, lr_update=None, update_wrap=None,
-                          rescale='maxabs', rng=None, val_imgs=None, record=None):
+                          rescale='maxabs', rng=None, val_imgs=None, record=None, gauge=None):
     """TNutils.py:1570-1631.  Full-batch unless batch_size < N (then `rng.shuffle` plays the role of
     np.random.shuffle(guide), :1601-1602).  Mutates `mps` (a list) in place; returns (cost, lr).
     `record(step_index, k, going_right, out)` is called after every step if given."""
@@ -488,7 +505,7 @@ def learning_epoch_cached(mps, imgs, epochs, lr, cache=None, batch_size=None, re
                 pk, pk1 = phys[:, k], phys[:, k + 1]
             cur_lr = getattr(lr, 'curr_lr', lr)
             out = two_site_step(mps, k, lv, rv, pk, pk1, cur_lr, going_right, renorm,
-                                max_bond, cutoff, update_wrap)
+                                max_bond, cutoff, update_wrap, gauge=gauge)
             write_back(mps, k, out['left'], out['right'])
             if going_right:
                 cache.advance_right(mps, k)

@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA engine (through the C-ABI in libbm.so) against the CPU oracle on identical
+seeded inputs, and against golden vectors produced by the real reference.
+
+Tolerances (BASELINE.json north_star): FP64 path 1e-6 relative on per-sample ln|psi| / NLL and singular
+values; sampled bit strings bit-exact given identical uniforms.  Most checks here are far tighter."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import born_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6      # the contract
+TIGHT = 1e-10    # what FP64 DMMA vs numpy actually achieves on these sizes
+
+
+@pytest.fixture(scope='module')
+def bm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import mps_born_machines_b200 as m
+    return m
+
+
+def make_problem(L, D, N, seed, d=2, p_on=0.4, centre=0):
+    rng = np.random.default_rng(seed)
+    mps = o.canonize(o.random_mps(L, D, d=d, rng=rng), centre)
+    if d == 2:
+        imgs = (rng.random((N, L)) < p_on).astype(np.int64)
+    else:
+        imgs = rng.integers(0, d, size=(N, L))
+    return mps, imgs
+
+
+def engine_for(bm, mps, imgs=None, cap=None):
+    d = mps[0].shape[-1]
+    cap = cap or max(o.bond_sizes(mps)) * d
+    eng = bm.BornEngine(len(mps), cap, phys_dim=d)
+    eng.set_mps(mps)
+    if imgs is not None:
+        eng.set_data(imgs)
+    return eng
+
+
+def normed(x):
+    return x / np.abs(x).max(axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize('L,D,N,seed', [(12, 6, 50, 1), (9, 5, 37, 2), (20, 7, 300, 3)])
+def test_site_roundtrip_and_env_build(bm, L, D, N, seed):
+    mps, imgs = make_problem(L, D, N, seed)
+    eng = engine_for(bm, mps, imgs)
+    for k in range(L):
+        assert np.array_equal(eng.get_site(k), mps[k])
+    cache = o.EnvCache(mps, o.embed(imgs), 'maxabs')
+    for k in (0, L // 2, L - 2):
+        eng.env_build(k)
+        for j in range(0, k + 1):
+            np.testing.assert_allclose(eng.env_get(0, j), normed(cache.lenv[j]), rtol=TIGHT, atol=1e-13)
+        for j in range(k + 2, L + 1):
+            np.testing.assert_allclose(eng.env_get(1, j), normed(cache.renv[j]), rtol=TIGHT, atol=1e-13)
+    eng.close()
+
+
+@pytest.mark.parametrize('L,D,N,seed,d', [(12, 6, 50, 11, 2), (10, 5, 129, 12, 2), (8, 4, 64, 13, 3), (8, 3, 40, 14, 4)])
+def test_step_grad_matches_oracle(bm, L, D, N, seed, d):
+    mps, imgs = make_problem(L, D, N, seed, d=d)
+    phys = o.embed(imgs, d)
+    eng = engine_for(bm, mps, imgs)
+    cache = o.EnvCache(mps, phys, 'pow2')
+    _, lp = o.logpsi(mps, phys)
+    for k in (0, 1, L // 2, L - 2):
+        S = eng.step_grad(k)
+        A = o.merge(mps, k)
+        np.testing.assert_allclose(eng.get_merged_at(k), A, rtol=TIGHT, atol=1e-14)
+        psi, S_ref = o.psi_and_grad(A, cache.lenv[k], cache.renv[k + 2], phys[:, k], phys[:, k + 1])
+        S_eng = eng.grad_to_ref(k, S)
+        np.testing.assert_allclose(S_eng, S_ref, rtol=1e-9, atol=1e-10 * np.abs(S_ref).max())
+        np.testing.assert_allclose(eng.last_logpsi(), lp, rtol=TIGHT)
+        tail = S[-2:].cpu().numpy()
+        assert abs(tail[0] - lp.sum()) < 1e-9 * abs(lp.sum()) and tail[1] == 0
+    eng.close()
+
+
+@pytest.mark.parametrize('renorm', ['max', 'l2'])
+@pytest.mark.parametrize('going_right', [True, False])
+def test_step_update_matches_oracle(bm, renorm, going_right):
+    L, D, N = 10, 6, 80
+    mps, imgs = make_problem(L, D, N, 21, centre=4 if going_right else 5)
+    phys = o.embed(imgs)
+    k = 4
+    eng = engine_for(bm, mps, imgs, cap=8)
+    cache = o.EnvCache(mps, phys, 'pow2')
+    ref = o.two_site_step(mps, k, cache.lenv[k], cache.renv[k + 2], phys[:, k], phys[:, k + 1], 0.05,
+                          going_right, renorm, max_bond=8)
+    out = eng.step(k, 0.05, going_right, renorm, max_bond=8, want_s=True, advance=False)
+    assert out['chi'] == ref['s'].size == 8
+    np.testing.assert_allclose(out['Z'], ref['Z'], rtol=TIGHT)
+    np.testing.assert_allclose(out['s_all'], ref['s_all'], rtol=RTOL)
+    np.testing.assert_allclose(out['s_all'], ref['s_all'], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(out['mean_dnll'], ref['dNLL'].mean(), rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(out['trunc_err'], np.sqrt(np.sum(ref['s_all'][8:] ** 2)), rtol=1e-8)
+    # factors are only defined up to the SVD gauge: compare the (gauge invariant) truncated product
+    new = list(mps)
+    o.write_back(new, k, ref['left'], ref['right'])
+    got_k, got_k1 = eng.get_site(k, squeeze=False), eng.get_site(k + 1, squeeze=False)
+    prod_ref = np.einsum('abp,bcq->apcq', o.site3(new, k), o.site3(new, k + 1))
+    prod_got = np.einsum('abp,bcq->apcq', got_k, got_k1)
+    np.testing.assert_allclose(prod_got, prod_ref, rtol=1e-8, atol=1e-11)
+    # isometry of the non-absorbed factor
+    if going_right:
+        np.testing.assert_allclose(np.einsum('abp,acp->bc', got_k, got_k), np.eye(8), atol=1e-12)
+    else:
+        np.testing.assert_allclose(np.einsum('abp,cbp->ac', got_k1, got_k1), np.eye(8), atol=1e-12)
+    eng.close()
+
+
+def test_cutoff_rule_and_bond_growth(bm):
+    """rank-deficient merged tensor: chi follows s_i > 1e-10 s_0 (>=1), capped by max_bond."""
+    L, N = 8, 40
+    mps, imgs = make_problem(L, 2, N, 31)
+    phys = o.embed(imgs)
+    eng = engine_for(bm, mps, imgs, cap=16)
+    mps_o = [t.copy() for t in mps]
+    cache = o.EnvCache(mps_o, phys, 'pow2')
+    going_right = True
+    for k in o.sweep_schedule(L):
+        ref = o.two_site_step(mps_o, k, cache.lenv[k], cache.renv[k + 2], phys[:, k], phys[:, k + 1], 0.3,
+                              going_right, 'max', max_bond=16, gauge='fixed')
+        o.write_back(mps_o, k, ref['left'], ref['right'])
+        if going_right:
+            cache.advance_right(mps_o, k)
+        else:
+            cache.advance_left(mps_o, k + 1)
+        out = eng.step(k, 0.3, going_right, 'max', max_bond=16, want_s=True)
+        assert out['chi'] == ref['s'].size, (k, out['chi'], ref['s'].size)
+        np.testing.assert_allclose(out['s'], ref['s'], rtol=RTOL)
+        if k == L - 2:
+            going_right = False
+    assert eng.bond_sizes() == o.bond_sizes(mps_o)
+    eng.close()
+
+
+def test_bars_and_stripes_trajectory(bm):
+    """Config 1: BAS 4x4, all 30 patterns, Dmax=16, 16 epochs: the engine follows the oracle's NLL curve."""
+    imgs = o.bars_n_stripes_all(4).astype(np.int64)
+    mps0 = o.canonize(o.random_mps(16, 2, rng=np.random.default_rng(1)), 0)
+    mps_o = [t.copy() for t in mps0]
+    # the reference's A/A.max() step (TNutils.py:1542) makes the trajectory depend on the SVD sign gauge:
+    # the oracle is put in the engine's deterministic gauge for this trajectory-level comparison
+    cost_o, _ = o.learning_epoch_cached(mps_o, imgs, 16, 0.5, batch_size=30, max_bond=16, lr_update=lambda l: l * 0.95,
+                                        gauge='fixed')
+    eng = engine_for(bm, mps0, imgs, cap=16)
+    lr = 0.5
+    cost = []
+    for _ in range(16):
+        eng.epoch(lr, 'max', max_bond=16)
+        cost.append(eng.nll(imgs, 0))
+        lr *= 0.95
+    np.testing.assert_allclose(cost, cost_o, rtol=RTOL)
+    # statistical pin (seed 1 converges in every sign gauge; seed 0 is gauge-sensitive)
+    assert abs(cost[-1] - 3.41) < 0.01                      # notebooks/bars_n_stripes.ipynb:664 -> 3.41098
+    assert eng.bond_sizes() == [2, 4, 8] + [16] * 9 + [8, 4, 2]
+    eng.close()
+
+
+def test_l2_trajectory_is_gauge_free(bm):
+    """with A/sqrt(A.A) (TNutils.py:1419) the trajectory is gauge invariant: the engine follows the plain
+    (LAPACK-gauge, reference-faithful) oracle over whole sweeps, including ragged bonds."""
+    L, N = 12, 60
+    mps0, imgs = make_problem(L, 3, N, 33)
+    mps_o = [t.copy() for t in mps0]
+    cost_o, _ = o.learning_epoch_cached(mps_o, imgs, 3, 0.05, renorm='l2', max_bond=7, cutoff=1e-8)
+    eng = engine_for(bm, mps0, imgs, cap=8)
+    cost = []
+    for _ in range(3):
+        eng.epoch(0.05, 'l2', max_bond=7, cutoff=1e-8)
+        cost.append(eng.nll(imgs, 0))
+    np.testing.assert_allclose(cost, cost_o, rtol=RTOL)
+    assert eng.bond_sizes() == o.bond_sizes(mps_o)
+    eng.close()
+
+
+def test_logpsi_matches_reference_golden(bm, golden_dir):
+    for tag in 'abc':
+        f = np.load(os.path.join(golden_dir, f'ref_psi_{tag}.npz'))
+        L = int(f['L'])
+        mps = [f[f'site{k}'] for k in range(L)]
+        eng = engine_for(bm, mps)
+        sg, ln = eng.logpsi(f['imgs'])
+        np.testing.assert_allclose(sg * np.exp(ln), f['psi'], rtol=1e-11)     # reference computepsi
+        eng.close()
+
+
+def test_logpsi_long_chain(bm):
+    mps, imgs = make_problem(784, 12, 200, 41, p_on=0.2)
+    eng = engine_for(bm, mps)
+    sg, ln = eng.logpsi(imgs)
+    s_o, l_o = o.logpsi(mps, o.embed(imgs))
+    np.testing.assert_allclose(ln, l_o, rtol=TIGHT)
+    assert np.array_equal(sg, s_o)
+    assert abs(eng.nll(imgs, 0) - o.compute_nll(mps, imgs, 0)) < 1e-9
+    eng.close()
+
+
+def test_generate_sample_matches_reference_golden(bm, golden_dir):
+    """bit strings of the reference's generate_sample (TNutils.py:1874) for 64 seeds, bit-exact."""
+    g = np.load(os.path.join(golden_dir, 'ref_generate_sample.npz'))
+    mps = [g[f'site{k}'] for k in range(20)]
+    eng = engine_for(bm, mps)
+    got = eng.sample(64, U=np.ascontiguousarray(g['uniforms'].T), rule='single')
+    assert np.array_equal(got, g['samples'])
+    eng.close()
+
+
+@pytest.mark.parametrize('L,D,N,seed', [(20, 8, 3000, 51), (33, 5, 777, 52)])
+def test_batched_sampler_bit_exact(bm, L, D, N, seed):
+    mps, _ = make_problem(L, D, 1, seed)
+    U = np.random.default_rng(seed + 1).random((L, N))
+    want = o.generate_samples(mps, U)
+    eng = engine_for(bm, mps)
+    got = eng.sample(N, U=U, rule='batched')
+    assert np.array_equal(got, want.astype(np.uint8))
+    eng.close()
+
+
+def test_device_uniform_generator_and_sampling(bm):
+    mps, _ = make_problem(16, 6, 1, 61)
+    eng = engine_for(bm, mps)
+    n = 500
+    got = eng.sample(n, U=None, seed=1234)
+    U = np.stack([bm.uniforms_reference(1234, s, n) for s in range(16)])
+    assert np.array_equal(got, o.generate_samples(mps, U).astype(np.uint8))
+    eng.close()
+
+
+def test_known_prefix_reconstruction(bm):
+    """reconstruct (TNutils.py:2053) with the bottom half unknown (partial_removal_img half=0)."""
+    L, D, N = 16, 6, 200
+    mps, imgs = make_problem(L, D, N, 71)
+    rng = np.random.default_rng(72)
+    start = 8
+    corr = imgs.copy(); corr[:, start:] = -1
+    U = rng.random((L - start, N))
+    eng = engine_for(bm, mps)
+    got = eng.sample(N, U=U, rule='single', prefix=corr, start_site=start)
+    for n in range(N):
+        want = o.reconstruct(mps, corr[n], U[:, n])
+        assert np.array_equal(got[n], want), n
+    eng.close()
+
+
+def test_minibatch_mask(bm):
+    L, D, N = 10, 5, 90
+    mps, imgs = make_problem(L, D, N, 81, centre=3)
+    phys = o.embed(imgs)
+    eng = engine_for(bm, mps, imgs)
+    cache = o.EnvCache(mps, phys, 'pow2')
+    mask = np.random.default_rng(5).permutation(N)[:25]
+    k = 3
+    S = eng.step_grad(k, mask)
+    A = o.merge(mps, k)
+    _, S_ref = o.psi_and_grad(A, cache.lenv[k][mask], cache.renv[k + 2][mask], phys[mask, k], phys[mask, k + 1])
+    np.testing.assert_allclose(eng.grad_to_ref(k, S), S_ref, rtol=1e-9, atol=1e-10 * np.abs(S_ref).max())
+    eng.close()
+
+
+def test_zero_psi_skips_update(bm):
+    """a sample with psi == 0 must raise the reference's skip-update condition (TNutils.py:1244-1254)."""
+    L = 6
+    mps, imgs = make_problem(L, 3, 10, 91)
+    mps = [t.copy() for t in mps]
+    m = o.site3(mps, 5).copy(); m[:, :, 0] = 0.0           # pixel 1 at the last site has zero amplitude
+    mps[5] = m[:, 0, :]
+    imgs[:, 5] = 0; imgs[3, 5] = 1
+    eng = engine_for(bm, mps, imgs)
+    before = eng.get_site(2)
+    out = eng.step(2, 0.1, True, 'l2', advance=False)
+    assert out['skipped'] and out['n_zero_psi'] == 1
+    assert np.array_equal(eng.get_site(2), before)
+    eng.close()
+
+
+def test_config2_mid_chain_steps(bm):
+    """Config 2 shapes: L=784, N=1000, D=100 — a few mid-chain steps against the oracle."""
+    L, D, N = 784, 100, 1000
+    rng = np.random.default_rng(7)
+    imgs = o.synthetic_images(N, L)
+    # random right-canonical MPS built directly (QR per site) with the centre moved to site 390
+    mps = o.canonize(o.random_mps(L, D, rng=rng), 390)
+    phys = o.embed(imgs)
+    eng = engine_for(bm, mps, imgs, cap=D)
+    cache = o.EnvCache(mps, phys, 'pow2')
+    mps_o = [t.copy() for t in mps]
+    _, lp = o.logpsi(mps_o, phys)
+    for i, k in enumerate(range(390, 394)):
+        ref = o.two_site_step(mps_o, k, cache.lenv[k], cache.renv[k + 2], phys[:, k], phys[:, k + 1], 1e-3,
+                              True, 'l2', max_bond=D)
+        sum_log_ref = (np.log(np.abs(ref['psi'])) + cache.ls_l[k] + cache.ls_r[k + 2]).sum()
+        o.write_back(mps_o, k, ref['left'], ref['right'])
+        cache.advance_right(mps_o, k)
+        out = eng.step(k, 1e-3, True, 'l2', max_bond=D, want_s=True)
+        if i == 0:
+            np.testing.assert_allclose(eng.last_logpsi(), lp, rtol=1e-9)
+        assert out['chi'] == ref['s'].size
+        np.testing.assert_allclose(out['s'], ref['s'], rtol=RTOL)
+        np.testing.assert_allclose(out['sum_logpsi'], sum_log_ref, rtol=RTOL)
+        np.testing.assert_allclose(out['Z'], ref['Z'], rtol=RTOL)
+    eng.close()
