@@ -318,7 +318,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--samples', type=int, default=0)
-    ap.add_argument('--svd', default='gesvdj')
+    ap.add_argument('--svd', default='gram', choices=['gram', 'gesvdj'])
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -66,6 +66,11 @@ struct bm_ctx {
   // step workspaces
   double *Aint = nullptr, *A2 = nullptr, *W = nullptr, *Ssv = nullptr, *U = nullptr, *V = nullptr, *G = nullptr, *sgn = nullptr;
   double* work = nullptr; size_t lwork = 0;
+  // Gram-split workspaces (BM_SVD_GRAM)
+  double *Gq = nullptr, *Yb[2] = {nullptr, nullptr}, *Tb[2] = {nullptr, nullptr}, *Tmp = nullptr, *lam = nullptr;
+  double* h_lam = nullptr;   // pinned
+  std::vector<double> h_s;
+  int gram_levels = 0;
   int* info = nullptr; int* iscal = nullptr;
   double *psi = nullptr, *winv = nullptr, *lnpsi = nullptr;
   double* ws = nullptr; int ws_slots = 0;
@@ -335,6 +340,9 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
   DALLOC(c->Aint, mA * ldA); DALLOC(c->A2, mA * ldA); DALLOC(c->G, mA * ldA + 2);
   DALLOC(c->W, mA * mA); DALLOC(c->U, mA * mA); DALLOC(c->V, mA * mA); DALLOC(c->Ssv, mA); DALLOC(c->sgn, mA);
   DALLOC(c->info, 1); DALLOC(c->iscal, 4);
+  DALLOC(c->Gq, mA * mA); DALLOC(c->Yb[0], mA * mA); DALLOC(c->Yb[1], mA * mA); DALLOC(c->Tb[0], mA * mA); DALLOC(c->Tb[1], mA * mA);
+  DALLOC(c->Tmp, mA * mA); DALLOC(c->lam, mA);
+  CU(cudaMallocHost((void**)&c->h_lam, (mA + 2) * sizeof(double)));
   DALLOC(c->partZ, RED_BLOCKS); DALLOC(c->part2, RED_BLOCKS * 4); DALLOC(c->scal, 8);
   CU(cudaMallocHost((void**)&c->h_scal, 8 * sizeof(double)));
   CU(cudaMallocHost((void**)&c->h_iscal, 4 * sizeof(int)));
@@ -347,13 +355,14 @@ int bm_destroy(bm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.U, c->chain.lnabs, c->chain.sign};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->h_iscal) cudaFreeHost(c->h_iscal);
+  if (c->h_lam) cudaFreeHost(c->h_lam);
   if (c->tev[0]) { cudaEventDestroy(c->tev[0]); cudaEventDestroy(c->tev[1]); }
   if (c->gesvdj) cusolverDnDestroyGesvdjInfo(c->gesvdj);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
@@ -619,17 +628,91 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
   return BM_OK;
 }
 
-// thin SVD of W (column-major mA x nA) -> Ssv, U (mA x r), V (nA x r)
-static int run_svd(bm_ctx* c, int mA, int nA) {
+// thin SVD of W (column-major mA x nA) -> Ssv, U (mA x r), V (nA x r)   [north_star: cuSOLVER gesvdj]
+static int run_svd_gesvdj(bm_ctx* c, int mA, int nA) {
   Timer t_(c, 5);
-  if (c->svd_method == BM_SVD_GESVDJ) {
+  int lw = 0;
+  LIB(cusolverDnDgesvdj_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, 1, mA, nA, c->W, mA, c->Ssv, c->U, mA, c->V, nA, &lw, c->gesvdj));
+  if ((size_t)lw > c->lwork) { DALLOC(c->work, (size_t)lw); c->lwork = (size_t)lw; }
+  LIB(cusolverDnDgesvdj(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, 1, mA, nA, c->W, mA, c->Ssv, c->U, mA, c->V, nA, c->work, lw, c->info, c->gesvdj));
+  return BM_OK;
+}
+
+// Gram split: eigen-decomposition (cuSOLVER syevd) of the Gram matrix on the ISOMETRIC side, so that factor is
+// orthonormal to machine precision; the absorbed factor is obtained by projection (no division by s).
+// Small singular values (below sqrt(tau) of the level's largest) are recovered by deflating the resolved
+// subspace and repeating on the remainder, which keeps the relative cutoff rule (1e-10) exact.
+//   c->W holds Y = (q x p, column-major): A^T when the left factor is the isometry (p = mA), A otherwise (p = nA).
+//   Outputs: isometry (p x r) and absorbed factor (q x chi) in c->U / c->V, singular values in c->h_s, chi.
+static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond, double cutoff, int* chi_out, double* trunc_out) {
+  Timer t_(c, 5);
+  constexpr double TAU = 1e-5;
+  const int p = going_right ? mA : nA, q = going_right ? nA : mA;
+  double* iso = going_right ? c->U : c->V;
+  double* absb = going_right ? c->V : c->U;
+  const int rmin = std::min(mA, nA);
+  const int need = std::min(max_bond > 0 ? max_bond : rmin, rmin);
+  const double one = 1.0, zero = 0.0;
+  std::vector<double>& sv = c->h_s;
+  sv.clear();
+  const double* Yl = c->W;
+  const double* T = nullptr;
+  int pl = p, lev = 0, yb = 0, tb = 0, ncols_out = 0;
+  double sigma0sq = 0.0;
+  while (true) {
+    ++lev;
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, pl, pl, q, &one, Yl, q, Yl, q, &zero, c->Gq, pl));
     int lw = 0;
-    LIB(cusolverDnDgesvdj_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, 1, mA, nA, c->W, mA, c->Ssv, c->U, mA, c->V, nA, &lw, c->gesvdj));
+    LIB(cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, pl, c->Gq, pl, c->lam, &lw));
     if ((size_t)lw > c->lwork) { DALLOC(c->work, (size_t)lw); c->lwork = (size_t)lw; }
-    LIB(cusolverDnDgesvdj(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, 1, mA, nA, c->W, mA, c->Ssv, c->U, mA, c->V, nA, c->work, lw, c->info, c->gesvdj));
-    return BM_OK;
+    LIB(cusolverDnDsyevd(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, pl, c->Gq, pl, c->lam, c->work, lw, c->info));
+    CU(cudaMemcpyAsync(c->h_lam, c->lam, (size_t)pl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_iscal + 2, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_iscal[2] != 0) return fail(c, BM_ECUSOLVER, "syevd failed (info=" + std::to_string(c->h_iscal[2]) + ")");
+    const double* lam = c->h_lam;
+    const double lmax = lam[pl - 1];
+    if (lev == 1) sigma0sq = lmax;
+    int kkeep = 0;
+    while (kkeep < pl && lam[pl - 1 - kkeep] > TAU * lmax) ++kkeep;
+    const int rest = pl - kkeep;
+    const bool done = ((int)sv.size() + kkeep >= need) || rest == 0 || !(lmax > 0.0) ||
+                      (TAU * lmax <= cutoff * cutoff * sigma0sq) || lev >= 8;
+    const int ncopy = done ? pl : kkeep;
+    const double* Qtop = c->Gq + (size_t)(pl - ncopy) * pl;           // eigenvectors of the ncopy largest, ascending
+    if (!T) {
+      k_cols_reverse_copy<<<148, 256, 0, c->stream>>>(Qtop, pl, pl, ncopy, iso + (size_t)ncols_out * p, p);
+    } else {
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, p, ncopy, pl, &one, T, p, Qtop, pl, &zero, c->Tmp, p));
+      k_cols_reverse_copy<<<148, 256, 0, c->stream>>>(c->Tmp, p, p, ncopy, iso + (size_t)ncols_out * p, p);
+    }
+    c->launches++;
+    for (int j = 0; j < ncopy; ++j) sv.push_back(std::sqrt(std::max(lam[pl - 1 - j], 0.0)));
+    ncols_out += ncopy;
+    if (done) break;
+    // deflate: continue on the unresolved subspace spanned by Q[:, 0:rest]
+    double* Yn = c->Yb[yb];
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, q, rest, pl, &one, Yl, q, c->Gq, pl, &zero, Yn, q));
+    double* Tn = c->Tb[tb];
+    if (!T) CU(cudaMemcpyAsync(Tn, c->Gq, (size_t)p * rest * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    else LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, p, rest, pl, &one, T, p, c->Gq, pl, &zero, Tn, p));
+    Yl = Yn; T = Tn; pl = rest; yb ^= 1; tb ^= 1;
   }
-  return fail(c, BM_EINVAL, "SVD method not implemented");
+  c->gram_levels = lev;
+  if ((int)sv.size() > rmin) sv.resize(rmin);
+  int chi;
+  if (cutoff > 0.0) {
+    chi = 0;
+    for (double x : sv) if (x > cutoff * sv[0]) ++chi;
+    chi = std::max(chi, 1);
+    if (max_bond > 0) chi = std::min(chi, max_bond);
+  } else chi = max_bond > 0 ? std::min(max_bond, (int)sv.size()) : (int)sv.size();
+  double t2 = 0.0;
+  for (size_t i = chi; i < sv.size(); ++i) t2 += sv[i] * sv[i];
+  *chi_out = chi; *trunc_out = std::sqrt(t2);
+  // absorbed factor by projection: Y . iso[:, :chi]   (= V s  or  U s)
+  LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, q, chi, p, &one, c->W, q, iso, p, &zero, absb, q));
+  return BM_OK;
 }
 
 int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
@@ -655,28 +738,40 @@ int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, do
     return fail(c, BM_EZERO_PSI, "psi == 0 for " + std::to_string((long long)nzero) + " samples; update skipped");
   }
 
+  const bool gram = c->svd_method == BM_SVD_GRAM;
   k_update<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, S_dev, c->partZ, rows, ldA, Dr, ldr, batch_total, lr, mom_bias, c->A2, c->part2, c->scal);
-  k_scale_to_colmajor<<<RED_BLOCKS * 4, 256, 0, c->stream>>>(c->A2, c->part2, rows, ldA, d, Dr, ldr, renorm, c->W, c->scal);
+  k_scale_to_colmajor<<<RED_BLOCKS * 4, 256, 0, c->stream>>>(c->A2, c->part2, rows, ldA, d, Dr, ldr, renorm,
+                                                             (gram && going_right) ? 1 : 0, c->W, c->scal);
   c->launches += 2;
   KCHECK();
-  int r = run_svd(c, rows, ncols);
-  if (r != BM_OK) return r;
-  k_chi<<<1, 32, 0, c->stream>>>(c->Ssv, rmin, cutoff, max_bond, c->info, c->iscal, c->scal);
-  c->launches++;
-  CU(cudaMemcpyAsync(c->h_iscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int chi = 0, info = 0;
+  double trunc = 0.0;
+  if (gram) {
+    int r = run_svd_gram(c, rows, ncols, going_right ? 1 : 0, max_bond, cutoff, &chi, &trunc);
+    if (r != BM_OK) return r;
+    c->h_iscal[0] = chi; c->h_iscal[1] = 0;
+    CU(cudaMemcpyAsync(c->iscal, c->h_iscal, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (s_host) std::memcpy(s_host, c->h_s.data(), std::min<size_t>(c->h_s.size(), rmin) * sizeof(double));
+  } else {
+    int r = run_svd_gesvdj(c, rows, ncols);
+    if (r != BM_OK) return r;
+    k_chi<<<1, 32, 0, c->stream>>>(c->Ssv, rmin, cutoff, max_bond, c->info, c->iscal, c->scal);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_iscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (s_host) CU(cudaMemcpyAsync(s_host, c->Ssv, (size_t)rmin * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaMemcpyAsync(c->h_scal, c->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (s_host) CU(cudaMemcpyAsync(s_host, c->Ssv, (size_t)rmin * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   k_gauge_signs<<<32, 256, 0, c->stream>>>(c->U, rows, d, Dl, c->iscal, c->sgn);
-  c->launches++;
-  k_factor_out<<<148 * 2, 256, 0, c->stream>>>(c->U, c->V, c->Ssv, c->sgn, c->iscal, d, Dl, Dr, going_right ? 1 : 0,
+  k_factor_out<<<148 * 2, 256, 0, c->stream>>>(c->U, c->V, c->Ssv, c->sgn, c->iscal, d, Dl, Dr, going_right ? 1 : 0, gram ? 1 : 0,
                                                c->Lf(k), c->Rf(k), c->Lf(k + 1), c->Rf(k + 1));
-  c->launches++;
+  c->launches += 2;
   KCHECK();
   CU(cudaStreamSynchronize(c->stream));
-  const int chi = c->h_iscal[0], info = c->h_iscal[1];
+  if (!gram) { chi = c->h_iscal[0]; info = c->h_iscal[1]; }
   if (scalars_host) {
     std::memcpy(scalars_host, c->h_scal, 8 * sizeof(double));
     scalars_host[1] = sumln; scalars_host[2] = nzero; scalars_host[3] = chi;
+    if (gram) scalars_host[6] = trunc;
   }
   c->sDr[k] = chi; c->sDl[k + 1] = chi;
   invalidate_site(c, k); invalidate_site(c, k + 1);

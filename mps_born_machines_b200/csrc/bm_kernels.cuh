@@ -699,10 +699,13 @@ __global__ void __launch_bounds__(256) k_update(const double* __restrict__ A, co
   }
 }
 
-// W (column-major, rows x (d*Dr), compact) = A2 / c, c = max(A2) or sqrt(sum A2^2).  scal[4]=mean dNLL, [5]=c, [7]=nonfinite
+// W = A2 / c, c = max(A2) or sqrt(sum A2^2), written compactly for the factorisation:
+//   transposed == 0: column-major (rows x ncols): W[cc*rows + r]          (cuSOLVER gesvdj input; Gram on the right side)
+//   transposed == 1: column-major (ncols x rows) = A^T: W[r*ncols + cc]    (Gram on the left side)
+// scal[4]=mean dNLL, [5]=c, [7]=nonfinite
 __global__ void __launch_bounds__(256) k_scale_to_colmajor(const double* __restrict__ A2, const double* __restrict__ part2,
                                                            int rows, int ldA, int d, int Dr, int ldRpad, int renorm,
-                                                           double* __restrict__ W, double* __restrict__ scal) {
+                                                           int transposed, double* __restrict__ W, double* __restrict__ scal) {
   __shared__ double cs;
   if (threadIdx.x == 0) {
     double mx = -INFINITY, ss = 0.0, sd = 0.0, nf = 0.0;
@@ -715,11 +718,22 @@ __global__ void __launch_bounds__(256) k_scale_to_colmajor(const double* __restr
   const double c = cs;
   const int ncols = d * Dr;
   const long long total = (long long)rows * ncols;
-  // consecutive threads walk consecutive rows of W (coalesced writes); reads are strided but L2-resident
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
-    int cc = (int)(e / rows), r = (int)(e % rows);
+    int cc, r;
+    if (transposed) { r = (int)(e / ncols); cc = (int)(e % ncols); }
+    else { cc = (int)(e / rows); r = (int)(e % rows); }
     int q = cc / Dr, cidx = cc % Dr;
     W[e] = A2[(long long)r * ldA + q * ldRpad + cidx] / c;
+  }
+}
+
+// dst[:, j] = src[:, ncols-1-j]   (eigenvectors come in ascending order; factors are stored descending)
+__global__ void __launch_bounds__(256) k_cols_reverse_copy(const double* __restrict__ src, int ld_src, int rows, int ncols,
+                                                           double* __restrict__ dst, int ld_dst) {
+  const long long total = (long long)rows * ncols;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    int j = (int)(e / rows), r = (int)(e % rows);
+    dst[(long long)j * ld_dst + r] = src[(long long)(ncols - 1 - j) * ld_src + r];
   }
 }
 
@@ -767,7 +781,7 @@ __global__ void __launch_bounds__(256) k_gauge_signs(const double* __restrict__ 
 __global__ void __launch_bounds__(256) k_factor_out(const double* __restrict__ U, const double* __restrict__ V,
                                                     const double* __restrict__ s, const double* __restrict__ sgn,
                                                     const int* __restrict__ iscal,
-                                                    int d, int Dl, int Dr, int going_right,
+                                                    int d, int Dl, int Dr, int going_right, int premult,
                                                     double* __restrict__ Lk, double* __restrict__ Rk,
                                                     double* __restrict__ Lk1, double* __restrict__ Rk1) {
   const int chi = iscal[0];
@@ -778,14 +792,14 @@ __global__ void __launch_bounds__(256) k_factor_out(const double* __restrict__ U
     if (e < nU) {
       int b = (int)(e / mA), pa = (int)(e % mA), p = pa / Dl, a = pa % Dl;
       double v = U[e] * sgn[b];
-      if (!going_right) v *= s[b];
+      if (!going_right && !premult) v *= s[b];
       Rk[((long long)b * d + p) * ldl + a] = v;
       Lk[((long long)a * d + p) * ldx + b] = v;
     } else {
       long long f = e - nU;
       int b = (int)(f / nA), qc = (int)(f % nA), q = qc / Dr, c = qc % Dr;
       double v = V[f] * sgn[b];
-      if (going_right) v *= s[b];
+      if (going_right && !premult) v *= s[b];
       Lk1[((long long)b * d + q) * ldr + c] = v;
       Rk1[((long long)c * d + q) * ldx + b] = v;
     }

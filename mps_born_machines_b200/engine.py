@@ -28,7 +28,7 @@ def sweep_schedule(L):
 
 
 class BornEngine:
-    def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gesvdj', dist_group=None):
+    def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gram', dist_group=None):
         if not torch.cuda.is_available():
             raise RuntimeError('BornEngine needs a CUDA device (sm_100a); there is no CPU fallback')
         self.L, self.d, self.Dcap = int(n_sites), int(phys_dim), int(max_bond)

@@ -35,10 +35,10 @@ def make_problem(L, D, N, seed, d=2, p_on=0.4, centre=0):
     return mps, imgs
 
 
-def engine_for(bm, mps, imgs=None, cap=None):
+def engine_for(bm, mps, imgs=None, cap=None, svd='gram'):
     d = mps[0].shape[-1]
     cap = cap or max(o.bond_sizes(mps)) * d
-    eng = bm.BornEngine(len(mps), cap, phys_dim=d)
+    eng = bm.BornEngine(len(mps), cap, phys_dim=d, svd=svd)
     eng.set_mps(mps)
     if imgs is not None:
         eng.set_data(imgs)
@@ -85,14 +85,15 @@ def test_step_grad_matches_oracle(bm, L, D, N, seed, d):
     eng.close()
 
 
+@pytest.mark.parametrize('svd', ['gram', 'gesvdj'])
 @pytest.mark.parametrize('renorm', ['max', 'l2'])
 @pytest.mark.parametrize('going_right', [True, False])
-def test_step_update_matches_oracle(bm, renorm, going_right):
+def test_step_update_matches_oracle(bm, renorm, going_right, svd):
     L, D, N = 10, 6, 80
     mps, imgs = make_problem(L, D, N, 21, centre=4 if going_right else 5)
     phys = o.embed(imgs)
     k = 4
-    eng = engine_for(bm, mps, imgs, cap=8)
+    eng = engine_for(bm, mps, imgs, cap=8, svd=svd)
     cache = o.EnvCache(mps, phys, 'pow2')
     ref = o.two_site_step(mps, k, cache.lenv[k], cache.renv[k + 2], phys[:, k], phys[:, k + 1], 0.05,
                           going_right, renorm, max_bond=8)
@@ -118,12 +119,13 @@ def test_step_update_matches_oracle(bm, renorm, going_right):
     eng.close()
 
 
-def test_cutoff_rule_and_bond_growth(bm):
+@pytest.mark.parametrize('svd', ['gram', 'gesvdj'])
+def test_cutoff_rule_and_bond_growth(bm, svd):
     """rank-deficient merged tensor: chi follows s_i > 1e-10 s_0 (>=1), capped by max_bond."""
     L, N = 8, 40
     mps, imgs = make_problem(L, 2, N, 31)
     phys = o.embed(imgs)
-    eng = engine_for(bm, mps, imgs, cap=16)
+    eng = engine_for(bm, mps, imgs, cap=16, svd=svd)
     mps_o = [t.copy() for t in mps]
     cache = o.EnvCache(mps_o, phys, 'pow2')
     going_right = True
@@ -142,6 +144,26 @@ def test_cutoff_rule_and_bond_growth(bm):
             going_right = False
     assert eng.bond_sizes() == o.bond_sizes(mps_o)
     eng.close()
+
+
+def test_gram_split_small_singular_values(bm):
+    """the Gram split must resolve singular values down to the 1e-10 relative cutoff (multi-level deflation)."""
+    L, D, N = 6, 12, 30
+    rng = np.random.default_rng(77)
+    mps, imgs = make_problem(L, D, N, 77, centre=2)
+    # give bond 2-3 a geometric spectrum spanning 14 decades by rescaling the centre's right bond
+    m = o.site3(mps, 2).copy()
+    m *= (0.01 ** np.arange(m.shape[1]))[None, :, None]
+    mps = [t.copy() for t in mps]; mps[2] = m
+    phys = o.embed(imgs)
+    cache = o.EnvCache(mps, phys, 'pow2')
+    for going_right in (True, False):
+        eng = engine_for(bm, mps, imgs, cap=24, svd='gram')
+        ref = o.two_site_step(mps, 2, cache.lenv[2], cache.renv[4], phys[:, 2], phys[:, 3], 1e-9, going_right, 'l2')
+        out = eng.step(2, 1e-9, going_right, 'l2', want_s=True, advance=False)
+        assert out['chi'] == ref['s'].size, (out['chi'], ref['s'].size)
+        np.testing.assert_allclose(out['s'], ref['s'], rtol=RTOL)
+        eng.close()
 
 
 def test_bars_and_stripes_trajectory(bm):
@@ -167,14 +189,15 @@ def test_bars_and_stripes_trajectory(bm):
     eng.close()
 
 
-def test_l2_trajectory_is_gauge_free(bm):
+@pytest.mark.parametrize('svd', ['gram', 'gesvdj'])
+def test_l2_trajectory_is_gauge_free(bm, svd):
     """with A/sqrt(A.A) (TNutils.py:1419) the trajectory is gauge invariant: the engine follows the plain
     (LAPACK-gauge, reference-faithful) oracle over whole sweeps, including ragged bonds."""
     L, N = 12, 60
     mps0, imgs = make_problem(L, 3, N, 33)
     mps_o = [t.copy() for t in mps0]
     cost_o, _ = o.learning_epoch_cached(mps_o, imgs, 3, 0.05, renorm='l2', max_bond=7, cutoff=1e-8)
-    eng = engine_for(bm, mps0, imgs, cap=8)
+    eng = engine_for(bm, mps0, imgs, cap=8, svd=svd)
     cost = []
     for _ in range(3):
         eng.epoch(0.05, 'l2', max_bond=7, cutoff=1e-8)
