@@ -96,6 +96,10 @@ int bm_step_update(bm_ctx* ctx, int k, const double* S_dev, double batch_total, 
                    int going_right, int max_bond, double cutoff, double mom_bias,
                    double* scalars_host, double* s_host);
 
+/* Merge + split of bond k without a gradient step or renormalisation: the primitive of `compress`,
+ * `compress_copy`, `compress2` (TNutils.py:930-993) and of SVD-based canonicalisation sweeps. */
+int bm_split_bond(bm_ctx* ctx, int k, int going_right, int max_bond, double cutoff, double* scalars_host, double* s_host);
+
 /* Download dNLL-ingredients for host-side update_wrap callbacks (TNutils.py:1541): the merged tensor A
  * of the last bm_step_grad in (Dl,d,Dr,d) row-major reference order, and upload a replacement update. */
 int bm_get_merged(bm_ctx* ctx, double* A_host);

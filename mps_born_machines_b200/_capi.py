@@ -30,6 +30,7 @@ _SIGS = [
     ('bm_step_grad', C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     ('bm_step_update', C.c_int, [_P, C.c_int, _P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
                                  C.c_double, _P, _P]),
+    ('bm_split_bond', C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]),
     ('bm_get_merged', C.c_int, [_P, _P]),
     ('bm_ref_to_engine', C.c_int, [_P, C.c_int, _P, _P]),
     ('bm_engine_to_ref', C.c_int, [_P, C.c_int, _P, _P]),

@@ -543,18 +543,12 @@ int bm_grad_dims(bm_ctx* c, int k, int* rows, int* ld, int* Dl, int* Dr, int* ld
   return BM_OK;
 }
 
-int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double* S_dev) {
-  if (!c) return BM_EINVAL;
-  REQUIRE(c->N > 0 && S_dev, "bm_step_grad: no training data / null output");
-  int r = check_bond(c, k);
-  if (r != BM_OK) return r;
-  r = bm_env_build(c, k);
-  if (r != BM_OK) return r;
-  const int d = c->d, G = d * d, N = c->N;
+// merge: A[(p,a),(q,c)] = sum_b M_k[a,b,p] M_{k+1}[b,c,q]  (TNutils.py:1526) — plain library GEMMs; also the
+// partial sums of Z = <A,A>
+static int merge_bond(bm_ctx* c, int k) {
+  const int d = c->d;
   const int Dl = c->sDl[k], chi0 = c->sDr[k], Dr = c->sDr[k + 1];
   const int ldx = even(chi0), ldr = even(Dr), ldA = d * ldr, rows = d * Dl;
-
-  // ---- merge: A[(p,a),(q,c)] = sum_b M_k[a,b,p] M_{k+1}[b,c,q]  (TNutils.py:1526) — plain library GEMMs
   {
     Timer t_(c, 4);
     const double one = 1.0, zero = 0.0;
@@ -568,6 +562,23 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
   }
   k_sumsq<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, rows, ldA, Dr, ldr, c->partZ);
   c->launches++;
+  KCHECK();
+  return BM_OK;
+}
+
+int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double* S_dev) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->N > 0 && S_dev, "bm_step_grad: no training data / null output");
+  int r = check_bond(c, k);
+  if (r != BM_OK) return r;
+  r = bm_env_build(c, k);
+  if (r != BM_OK) return r;
+  const int d = c->d, G = d * d, N = c->N;
+  const int Dl = c->sDl[k], chi0 = c->sDr[k], Dr = c->sDr[k + 1];
+  const int ldx = even(chi0), ldr = even(Dr), ldA = d * ldr, rows = d * Dl;
+
+  r = merge_bond(c, k);
+  if (r != BM_OK) return r;
 
   // ---- grouping for this step: all samples (precomputed) or a minibatch
   const int* perm; const int* goff; const int* h_goff; int B;
@@ -715,6 +726,10 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
   return BM_OK;
 }
 
+static int update_tail(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
+                       int going_right, int max_bond, double cutoff, double mom_bias,
+                       double* scalars_host, double* s_host, double sumln, double nzero);
+
 int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
                    int going_right, int max_bond, double cutoff, double mom_bias,
                    double* scalars_host, double* s_host) {
@@ -738,6 +753,16 @@ int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, do
     return fail(c, BM_EZERO_PSI, "psi == 0 for " + std::to_string((long long)nzero) + " samples; update skipped");
   }
 
+  return update_tail(c, k, S_dev, batch_total, lr, renorm, going_right, max_bond, cutoff, mom_bias, scalars_host, s_host, sumln, nzero);
+}
+
+static int update_tail(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
+                       int going_right, int max_bond, double cutoff, double mom_bias,
+                       double* scalars_host, double* s_host, double sumln, double nzero) {
+  const int d = c->d;
+  const int Dl = c->sDl[k], Dr = c->sDr[k + 1];
+  const int ldr = even(Dr), ldA = d * ldr, rows = d * Dl, ncols = d * Dr;
+  const int rmin = std::min(rows, ncols);
   const bool gram = c->svd_method == BM_SVD_GRAM;
   k_update<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, S_dev, c->partZ, rows, ldA, Dr, ldr, batch_total, lr, mom_bias, c->A2, c->part2, c->scal);
   k_scale_to_colmajor<<<RED_BLOCKS * 4, 256, 0, c->stream>>>(c->A2, c->part2, rows, ldA, d, Dr, ldr, renorm,
@@ -779,6 +804,23 @@ int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, do
   if (c->h_scal[7] > 0) return fail(c, BM_ENONFINITE, "non-finite entries in the updated merged tensor");
   if (info != 0) return fail(c, BM_ECUSOLVER, "SVD did not converge (info=" + std::to_string(info) + ")");
   return BM_OK;
+}
+
+// merge + split only (no gradient step, no renormalisation): compress / canonicalisation sweeps
+// (TNutils.py:930-993 `compress*`: A.split(..., absorb='left', max_bond=...)).
+int bm_split_bond(bm_ctx* c, int k, int going_right, int max_bond, double cutoff, double* scalars_host, double* s_host) {
+  if (!c) return BM_EINVAL;
+  int r = check_bond(c, k);
+  if (r != BM_OK) return r;
+  CU(cudaSetDevice(c->device));
+  r = merge_bond(c, k);
+  if (r != BM_OK) return r;
+  const int d = c->d, Dl = c->sDl[k], Dr = c->sDr[k + 1];
+  const size_t cnt = (size_t)d * Dl * d * even(Dr);
+  CU(cudaMemsetAsync(c->G, 0, cnt * sizeof(double), c->stream));
+  if (max_bond > c->Dcap || max_bond <= 0) max_bond = c->Dcap;
+  c->last_k = k;
+  return update_tail(c, k, c->G, 1.0, 0.0, 2 /* no renormalisation */, going_right, max_bond, cutoff, 0.0, scalars_host, s_host, 0.0, 0.0);
 }
 
 int bm_get_merged(bm_ctx* c, double* A_host) {

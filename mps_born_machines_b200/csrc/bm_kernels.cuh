@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(256) k_scale_to_colmajor(const double* __restr
   if (threadIdx.x == 0) {
     double mx = -INFINITY, ss = 0.0, sd = 0.0, nf = 0.0;
     for (int i = 0; i < RED_BLOCKS; ++i) { mx = fmax(mx, part2[i * 4]); ss += part2[i * 4 + 1]; sd += part2[i * 4 + 2]; nf += part2[i * 4 + 3]; }
-    double c = renorm == 0 ? mx : sqrt(ss);
+    double c = renorm == 0 ? mx : (renorm == 1 ? sqrt(ss) : 1.0);
     cs = c;
     if (blockIdx.x == 0) { scal[4] = sd / ((double)rows * d * Dr); scal[5] = c; scal[7] = nf; }
   }

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import _capi
+from .parallel import allreduce_sum_
 from ._capi import RENORM, RULE, SVD, ZeroPsiError, check, lib
 
 SCALAR_NAMES = ('Z', 'sum_logpsi', 'n_zero_psi', 'chi', 'mean_dnll', 'renorm_div', 'trunc_err', 'nonfinite')
@@ -169,13 +170,26 @@ class BornEngine:
         """One learning_step_cached + write-back + sequential_update (TNutils.py:1603-1620)."""
         S = self.step_grad(k, mask)
         if self.world > 1:
-            torch.distributed.all_reduce(S, group=self.group)   # sum over sample shards (NCCL over NVLink)
+            allreduce_sum_(S, self.group)   # sum over sample shards (NCCL over NVLink)
         if batch_total is None:
             batch_total = self.N_total if mask is None else len(mask) * self.world
         out = self.step_update(k, S, batch_total, lr, going_right, renorm, max_bond, cutoff, mom_bias, want_s)
         if advance:
             self.env_advance(k, going_right)
         out['nll_batch'] = -2.0 * out['sum_logpsi'] / batch_total + math.log(out['Z']) if out['Z'] > 0 else float('nan')
+        return out
+
+    def split_bond(self, k, going_right=False, max_bond=None, cutoff=1e-10, want_s=False):
+        """merge + truncated split of bond k, no gradient step (compress, TNutils.py:930-947)."""
+        rows, ld, Dl, Dr, _ = self.grad_dims(k)
+        scal = np.zeros(8)
+        s = np.empty(min(rows, self.d * Dr)) if want_s else None
+        check(self._ctx, self._lib.bm_split_bond(self._ctx, k, 1 if going_right else 0, int(max_bond) if max_bond else 0,
+                                                 float(cutoff), _ptr(scal), _ptr(s) if want_s else None))
+        out = dict(zip(SCALAR_NAMES, scal))
+        out['chi'] = int(out['chi'])
+        if want_s:
+            out['s'] = s[:out['chi']]
         return out
 
     def learning_step_host(self, k, site_k, site_k1, lr, going_right=True, **kw):

@@ -492,6 +492,10 @@ def learning_epoch_cached(mps, imgs, epochs, lr, cache=None, batch_size=None, re
     guide = np.arange(n)
     cost = []
     step_no = 0
+    # TNutils.py:1591 `lr = copy.copy(initial_lr)`: an mps_lr passed as lr is (shallow-)copied, so an update_wrap
+    # closure that refers to the caller's object sees t == 0 forever (momentum never activates in the notebooks)
+    import copy as _copy
+    lr = _copy.copy(lr)
     for _ in range(epochs):
         going_right = True
         for k in sweep_schedule(L):

@@ -1,0 +1,128 @@
+"""GPU tests of the TNutils-compatible facade: the reference notebooks' call sequences run unchanged."""
+import numpy as np
+import pytest
+
+from oracle import born_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def T():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from mps_born_machines_b200 import TNutils
+    return TNutils
+
+
+def test_bars_and_stripes_notebook_flow(T):
+    """notebooks/bars_n_stripes.ipynb cells 3-4, 11 (old arity of learning_epoch_cached)."""
+    np.random.seed(3)
+    bars_mps = T.initialize_mps(4 * 4, 2)
+    dataset = np.array(T.bars_n_stripes(30))
+    bar_data = np.array([T.tens_picture(img.flatten()) for img in dataset])
+    bar_cache = T.left_right_cache(bars_mps, bar_data)
+    start = [t.copy() for t in bars_mps.arrays()]
+    nlls, _ = T.learning_epoch_cached(bars_mps, bar_data, 16, 0.5, bar_cache, lr_update=lambda x: x * 0.95,
+                                      batch_size=30, max_bond=16)
+    assert len(nlls) == 16 and all(b <= a + 1e-9 for a, b in zip(nlls, nlls[1:]))
+    assert np.log(30) < nlls[-1] < np.log(30) + 0.1          # published: 3.41098 vs ln 30 = 3.4012
+    assert bars_mps.bond_sizes() == [2, 4, 8] + [16] * 9 + [8, 4, 2]
+    # same trajectory as the oracle in the engine's gauge
+    imgs = np.array([d.flatten() for d in dataset])
+    cost_o, _ = o.learning_epoch_cached(start, imgs, 16, 0.5, batch_size=30, max_bond=16,
+                                        lr_update=lambda x: x * 0.95, gauge='fixed')
+    np.testing.assert_allclose(nlls, cost_o, rtol=1e-6)
+    # computeNLL on the trained model (centre at site 0 after the sweep)
+    assert abs(T.computeNLL(bars_mps, imgs, 0) - nlls[-1]) < 1e-9
+    assert abs(T.computeNLL(bars_mps, imgs) - nlls[-1]) < 1e-8
+    samples = T.generate_samples(bars_mps, 100)
+    assert samples.shape == (100, 16)
+    valid = set(map(bytes, o.bars_n_stripes_all(4).astype(np.uint8)))
+    frac = np.mean([bytes(s.astype(np.uint8)) in valid for s in samples])
+    assert frac > 0.9                                        # a trained BAS model mostly emits valid patterns
+
+
+def test_momentum_flow_matches_oracle(T):
+    """bars_n_stripes.ipynb cell 6: mps_lr annealing + the scalar-mean momentum through update_wrap."""
+    np.random.seed(4)
+    mps = T.initialize_mps(16, 2)
+    start = [t.copy() for t in mps.arrays()]
+    imgs = o.bars_n_stripes_all(4)
+    data = np.array([T.tens_picture(img) for img in imgs])
+    cache = T.left_right_cache(mps, data)
+    sav_lr = T.mps_lr(mps, 0.5, 0.6, -np.log(0.95))
+    update_wrap = lambda site, div: sav_lr.J(site, div)
+    nlls, out_lr = T.learning_epoch_cached(mps, data, 4, sav_lr, cache, lr_update=T.lr_update,
+                                           update_wrap=update_wrap, batch_size=30, max_bond=16)
+    olr = o.MpsLr(16, 0.5, 0.6, -np.log(0.95))
+    def o_update(lr):
+        lr.new_epoch(); return lr
+    cost_o, _ = o.learning_epoch_cached(start, imgs, 4, olr, batch_size=30, max_bond=16, lr_update=o_update,
+                                        update_wrap=lambda k, dn: olr.J(k, dn), gauge='fixed')
+    np.testing.assert_allclose(nlls, cost_o, rtol=1e-6)
+    assert out_lr.t == 4 and abs(out_lr.curr_lr - 0.5 * 0.95 ** 4) < 1e-12
+
+
+def test_step_by_step_api(T):
+    """learning_step_cached + manual write-back + sequential_update (TNutils.py:1603-1620 as a user would)."""
+    np.random.seed(5)
+    L, N = 10, 24
+    mps = T.initialize_mps(L, 4)
+    imgs = (np.random.random((N, L)) < 0.4).astype(int)
+    data = np.array([T.tens_picture(img) for img in imgs])
+    cache = T.left_right_cache(mps, data, max_bond=8)
+    mps_o = [t.copy() for t in mps.arrays()]
+    phys = o.embed(imgs)
+    oc = o.EnvCache(mps_o, phys, 'pow2')
+    nll0 = T.computeNLL_cached(mps, data, cache, 0)
+    assert abs(nll0 - o.compute_nll(mps_o, imgs, 0)) < 1e-9
+    for index in range(0, 4):
+        A = T.learning_step_cached(mps, index, data, 0.05, cache, True, renorm='l2', max_bond=8)
+        ref = o.two_site_step(mps_o, index, oc.lenv[index], oc.renv[index + 2], phys[:, index], phys[:, index + 1],
+                              0.05, True, 'l2', max_bond=8)
+        assert A.tensors[0].data.shape == (ref['left'].shape[1:] if index == 0 else ref['left'].shape)
+        if index == 0:
+            mps.tensors[index].modify(data=np.transpose(A.tensors[0].data, (1, 0)))
+        else:
+            mps.tensors[index].modify(data=np.transpose(A.tensors[0].data, (0, 2, 1)))
+        mps.tensors[index + 1].modify(data=A.tensors[1].data)
+        T.sequential_update(mps, data, cache, index, True)
+        o.write_back(mps_o, index, ref['left'], ref['right']); oc.advance_right(mps_o, index)
+        np.testing.assert_allclose(A.info['Z'], ref['Z'], rtol=1e-9)
+    assert abs(T.computeNLL(mps, imgs) - o.compute_nll(mps_o, imgs)) < 1e-8
+    assert abs(T.computepsi(mps, imgs[0]) ** 2 - np.exp(2 * o.logpsi(mps_o, phys[:1])[1][0])) < 1e-9 * T.computepsi(mps, imgs[0]) ** 2
+
+
+def test_compress(T):
+    np.random.seed(6)
+    mps = T.initialize_mps(12, 8)
+    ref = o.compress([t.copy() for t in mps.arrays()], 4)
+    small = T.compress_copy(mps, 4)
+    assert small.bond_sizes() == o.bond_sizes(ref) and mps.max_bond() == 8
+    assert abs((small @ small) - o.norm2_full(ref)) < 1e-9
+    assert abs(small @ mps - np.exp(0.5 * 0) * (T.MPS(ref) @ mps)) < 1e-9          # same truncated state
+    T.compress2(mps, 4)
+    assert mps.max_bond() == 4
+
+
+def test_generate_sample_and_reconstruct(T):
+    np.random.seed(7)
+    mps = T.initialize_mps(16, 6)
+    arrays = [t.copy() for t in mps.arrays()]
+    np.random.seed(11)
+    got = T.generate_sample(mps)
+    np.random.seed(11)
+    u = [np.random.rand() for _ in range(16)]
+    assert got == o.generate_sample(o.right_canonize(arrays), u)
+    img = np.array(got)
+    corr = T.partial_removal_img(img, (4, 4), .5, 0, 0)
+    assert (corr[8:] == -1).all()
+    np.random.seed(12)
+    rec = T.reconstruct(mps, corr)
+    np.random.seed(12)
+    u = [np.random.rand() for _ in range(8)]
+    assert np.array_equal(rec, o.reconstruct(arrays, corr, u))
+    with pytest.raises(NotImplementedError):
+        T.reconstruct(mps, T.partial_removal_img(img, (4, 4), .5, 0, 1))
