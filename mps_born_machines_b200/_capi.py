@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, '_lib', 'libbm.so')
+LIB_PATH = os.environ.get('BM_LIB_PATH') or os.path.join(HERE, '_lib', 'libbm.so')   # BM_LIB_PATH: tuning variants
 
 BM_OK, BM_EINVAL, BM_ECUDA, BM_ECUSOLVER, BM_EZERO_PSI, BM_ENONFINITE, BM_ENOMEM = range(7)
 RENORM = {'max': 0, 'l2': 1}

@@ -19,18 +19,21 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build a tuning variant (e.g. defines=['-DBM_STAGES=3'], out='libbm_s3.so'); selected at run time
+    with the BM_LIB_PATH environment variable."""
+    out = OUT if out is None else os.path.join(HERE, '_lib', out)
+    if not force and out == OUT and not needs_build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + (['-Xptxas', '-v'] if verbose else []) + ['-o', out, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == '__main__':

@@ -28,6 +28,7 @@ struct Chain {            // ping-pong state for left chains (logpsi, sampler)
   uint8_t* phys = nullptr;   // [L][n]
   int* perm = nullptr;       // [n]
   int* goff = nullptr;       // [d+1]
+  int* goff_all = nullptr;   // {0, n}
   double* U = nullptr;       // uniforms
   size_t Ucap = 0;
   double* lnabs = nullptr; double* sign = nullptr;
@@ -45,6 +46,7 @@ struct bm_ctx {
   gesvdjInfo_t gesvdj = nullptr;
   int svd_method = BM_SVD_GESVDJ;
   long long launches = 0;
+  int n_sm = 148, panel_ctas = 296;
 
   // site tensors, two storage forms each (see k_factor_out)
   double* Lform = nullptr; double* Rform = nullptr; size_t site_stride = 0;
@@ -155,37 +157,32 @@ int ensure_stage(bm_ctx* c, size_t count) {
   return BM_OK;
 }
 
-inline int pick_tm(int n) {
-  if (n >= 148 * 2 * 64) return 64;
-  if (n >= 148 * 32) return 32;
-  return 16;
-}
-inline int max_tiles(int n, int tm, int ngroups) { return (n + tm - 1) / tm + ngroups; }
-
-template <int TM> constexpr size_t panel_smem() { return sizeof(PanelSmem<TM>); }
+constexpr size_t PANEL_SMEM = sizeof(PanelSmem<64>);
 
 int set_func_attrs(bm_ctx* c) {
-  CU(cudaFuncSetAttribute(k_env_advance<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<16>()));
-  CU(cudaFuncSetAttribute(k_env_advance<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<32>()));
-  CU(cudaFuncSetAttribute(k_env_advance<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<64>()));
-  CU(cudaFuncSetAttribute(k_psi<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<16>()));
-  CU(cudaFuncSetAttribute(k_psi<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<32>()));
-  CU(cudaFuncSetAttribute(k_psi<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<64>()));
-  CU(cudaFuncSetAttribute(k_sample_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<16>()));
-  CU(cudaFuncSetAttribute(k_sample_step<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<32>()));
-  CU(cudaFuncSetAttribute(k_sample_step<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<64>()));
+  CU(cudaFuncSetAttribute(k_env_advance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+  CU(cudaFuncSetAttribute(k_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+  CU(cudaFuncSetAttribute(k_sample_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
   CU(cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradSmem)));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c->device));
+  c->n_sm = prop.multiProcessorCount;
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_psi, NTHREADS, PANEL_SMEM));
+  c->panel_ctas = std::max(1, occ) * c->n_sm;
   return BM_OK;
+}
+
+// persistent panel kernels: one CTA per resident slot, never more CTAs than 16-row work units
+inline int panel_grid(bm_ctx* c, int nrows, int ngroups) {
+  int units = (nrows + UNIT - 1) / UNIT + ngroups;
+  return std::max(1, BM_PERSIST ? std::min(c->panel_ctas, units) : units);
 }
 
 // ---- launch helpers -------------------------------------------------------------------------------
 int launch_advance(bm_ctx* c, const AdvParams& P, int nrows) {
   Timer t_(c, 0);
-  int tm = pick_tm(nrows);
-  int grid = max_tiles(nrows, tm, P.gs.ngroups);
-  if (tm == 64) k_env_advance<64><<<grid, NTHREADS, panel_smem<64>(), c->stream>>>(P);
-  else if (tm == 32) k_env_advance<32><<<grid, NTHREADS, panel_smem<32>(), c->stream>>>(P);
-  else k_env_advance<16><<<grid, NTHREADS, panel_smem<16>(), c->stream>>>(P);
+  k_env_advance<<<panel_grid(c, nrows, P.gs.ngroups), NTHREADS, PANEL_SMEM, c->stream>>>(P);
   c->launches++;
   KCHECK();
   return BM_OK;
@@ -246,6 +243,8 @@ int chain_alloc(bm_ctx* c, int n) {
   DALLOC(ch.phys, (size_t)c->L * n);
   DALLOC(ch.perm, n);
   DALLOC(ch.goff, c->d + 1);
+  DALLOC(ch.goff_all, 2);
+  { int h[2] = {0, n}; CU(cudaMemcpy(ch.goff_all, h, sizeof(h), cudaMemcpyHostToDevice)); }
   DALLOC(ch.lnabs, n);
   DALLOC(ch.sign, n);
   ch.n = n;
@@ -358,7 +357,7 @@ int bm_destroy(bm_ctx* c) {
                   c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
-                  c->chain.goff, c->chain.U, c->chain.lnabs, c->chain.sign};
+                  c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->h_iscal) cudaFreeHost(c->h_iscal);
@@ -605,10 +604,7 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     P.gs = GroupSpec{perm, goff, G, d, (long long)Dl * ldA, (long long)ldr};
     P.cumeL = c->cume_slot(k); P.cumeR = c->cume_slot(k + 2);
     P.psi = c->psi; P.winv = c->winv; P.lnpsi = c->lnpsi;
-    int tm = pick_tm(B), grid = max_tiles(B, tm, G);
-    if (tm == 64) k_psi<64><<<grid, NTHREADS, panel_smem<64>(), c->stream>>>(P);
-    else if (tm == 32) k_psi<32><<<grid, NTHREADS, panel_smem<32>(), c->stream>>>(P);
-    else k_psi<16><<<grid, NTHREADS, panel_smem<16>(), c->stream>>>(P);
+    k_psi<<<panel_grid(c, B, G), NTHREADS, PANEL_SMEM, c->stream>>>(P);
     c->launches++;
     KCHECK();
   }
@@ -617,19 +613,30 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     const int tiles_a = (Dl + GT - 1) / GT, tiles_c = (Dr + GT - 1) / GT;
     int maxg = 0;
     for (int g = 0; g < G; ++g) maxg = std::max(maxg, h_goff[g + 1] - h_goff[g]);
-    long long work = (long long)B * tiles_a * tiles_c;
-    int kchunk = (int)((work + 2 * 148 - 1) / (2 * 148));
-    kchunk = std::max(KC, std::min(GRAD_MAXCHUNK, ((kchunk + KC - 1) / KC) * KC));
-    int nsplit = (maxg + kchunk - 1) / kchunk;
-    while (nsplit > c->ws_slots) { kchunk += KC; nsplit = (maxg + kchunk - 1) / kchunk; }
-    REQUIRE(kchunk <= GRAD_MAXCHUNK, "bm_step_grad: gradient workspace too small");
+    // samples per split: minimise the makespan  ceil(items / #SM) * kchunk  over multiples of 16
+    int kchunk = KC, nsplit = 0;
+    {
+      double best = 1e300;
+      for (int kc = KC; kc <= GRAD_MAXCHUNK; kc += KC) {
+        long long items = 0; int ns = 0;
+        for (int g = 0; g < G; ++g) {
+          int sg = (h_goff[g + 1] - h_goff[g] + kc - 1) / kc;
+          items += (long long)sg * tiles_a * tiles_c; ns = std::max(ns, sg);
+        }
+        if (ns > c->ws_slots) continue;
+        double waves = std::ceil((double)items / c->n_sm);
+        double cost = waves * (kc + 24.0);            // + fixed per-item cost (prologue, partial-tile store)
+        if (cost < best) { best = cost; kchunk = kc; nsplit = ns; }
+      }
+    }
+    REQUIRE(nsplit > 0 || maxg == 0, "bm_step_grad: gradient workspace too small");
     GradParams P{};
     P.Lenv = c->slot(k); P.ldL = c->ldcap; P.Dl = Dl;
     P.Renv = c->slot(k + 2); P.ldR = c->ldcap; P.Dr = Dr;
     P.winv = c->winv; P.perm = perm; P.goff = goff; P.ngroups = G; P.d = d;
     P.kchunk = kchunk; P.ws = c->ws; P.ws_stride = (long long)rows * ldA; P.ldA = ldA; P.ldRpad = ldr; P.tiles_c = tiles_c;
     dim3 grid(std::max(nsplit, 1), tiles_a * tiles_c, G);
-    { Timer t_(c, 2); k_grad<<<grid, NTHREADS, sizeof(GradSmem), c->stream>>>(P); }
+    { Timer t_(c, 2); k_grad<<<grid, GRAD_THREADS, sizeof(GradSmem), c->stream>>>(P); }
     { Timer t_(c, 3); k_grad_reduce<<<148 * 4, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, S_dev); }
     k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, S_dev + (size_t)rows * ldA);
     c->launches += 3;
@@ -907,7 +914,7 @@ static int sample_loop(bm_ctx* c, int n, int rule, int start_site, const double*
     if (ch.Ucap < nsites * n) { DALLOC(ch.U, nsites * n); ch.Ucap = nsites * n; }
     CU(cudaMemcpyAsync(ch.U, U_host, nsites * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   } else if (ch.Ucap < (size_t)n) { DALLOC(ch.U, n); ch.Ucap = n; }
-  const int tm = pick_tm(n), grid = (n + tm - 1) / tm;
+  const int grid = panel_grid(c, n, 1);
   for (int s = start_site; s < L; ++s) {
     const double* Us = ch.U;
     if (U_host) Us = ch.U + (size_t)(s - start_site) * n;
@@ -924,11 +931,10 @@ static int sample_loop(bm_ctx* c, int n, int rule, int start_site, const double*
     P.U = Us; P.pix_out = ch.phys + (size_t)s * n;
     P.n = n; P.strict = rule == BM_RULE_SINGLE; P.pix_first = rule == BM_RULE_BATCHED ? 1 : 0;
     P.both_norm = (s == start_site);
+    P.goff = ch.goff_all;
     {
       Timer t_(c, 7);
-      if (tm == 64) k_sample_step<64><<<grid, NTHREADS, panel_smem<64>(), c->stream>>>(P);
-      else if (tm == 32) k_sample_step<32><<<grid, NTHREADS, panel_smem<32>(), c->stream>>>(P);
-      else k_sample_step<16><<<grid, NTHREADS, panel_smem<16>(), c->stream>>>(P);
+      k_sample_step<<<grid, NTHREADS, PANEL_SMEM, c->stream>>>(P);
     }
     c->launches++;
     cur ^= 1;

@@ -19,7 +19,27 @@ namespace bm {
 constexpr int KC = 16;          // k-chunk (doubles) per pipeline stage
 constexpr int TN = 128;         // column tile
 constexpr int NTHREADS = 256;   // 8 warps arranged 2 (rows) x 4 (cols)
-constexpr int STAGES = 3;
+#ifndef BM_STAGES
+#define BM_STAGES 4
+#endif
+#ifndef BM_UNIT
+#define BM_UNIT 32
+#endif
+#ifndef BM_PERSIST
+#define BM_PERSIST 1
+#endif
+#ifndef BM_FASTPATH
+#define BM_FASTPATH 1
+#endif
+#ifndef BM_MINBLOCKS
+#define BM_MINBLOCKS 2
+#endif
+#ifndef BM_NOEPI
+#define BM_NOEPI 0      // tuning only: skip epilogue memory traffic
+#endif
+constexpr int STAGES = BM_STAGES;       // panel kernels: 4 x 27 KB = 106 KB -> still 2 CTAs / SM
+constexpr int UNIT = BM_UNIT;           // rows per scheduling unit (16, 32 or 64)
+constexpr int GSTAGES = 3;      // gradient kernel ring
 constexpr int A_STRIDE = KC + 4;   // 20: row stride (doubles) == 4 mod 16 -> conflict-free 8x4 fragment reads
 constexpr int B_STRIDE = TN + 4;   // 132
 constexpr double LN2 = 0.69314718055994530942;
@@ -84,50 +104,131 @@ __device__ __forceinline__ bool locate_tile(const GroupSpec& gs, int& g, int& ro
   return true;
 }
 
-// acc (TM x TN tile, this thread's fragments) = rows(rowptr)[:, 0:Din] . B[0:Din, col0:col0+TN]
-// B element (k, n) at B[k*ldB + n].  All 256 threads must call.  Requires 16-byte aligned row starts.
-template <int TM>
-__device__ __forceinline__ void panel_gemm(PanelSmem<TM>& sm, const double* const* rowptr, int Din,
-                                           const double* __restrict__ B, int ldB, int col0, int Dout,
-                                           double (&acc)[TM / 16][4][2]) {
+
+// Persistent, balanced tile scheduling.  Work is cut into units of 16 rows (never straddling a group); CTA c of P
+// owns units [c*U/P, (c+1)*U/P) and walks them in tiles of 64 / 32 / 16 rows, so every CTA gets the same work to
+// within one unit (a plain grid of 64-row tiles leaves a 3.18-wave tail at N = 60 000: -20 %).
+template <class F>
+__device__ __forceinline__ void for_each_tile(const int* __restrict__ goff, int ngroups, F&& f) {
+  long long U = 0;
+  for (int g = 0; g < ngroups; ++g) U += (goff[g + 1] - goff[g] + UNIT - 1) / UNIT;
+  const long long u0 = (long long)blockIdx.x * U / gridDim.x, u1 = (long long)(blockIdx.x + 1) * U / gridDim.x;
+  long long acc = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const int gb = goff[g], ge = goff[g + 1];
+    const long long ug = (ge - gb + UNIT - 1) / UNIT;
+    const long long lo = u0 > acc ? u0 : acc, hi = u1 < acc + ug ? u1 : acc + ug;
+    if (lo < hi) {
+      int row = gb + (int)(lo - acc) * UNIT;
+      const int rend = min(ge, gb + (int)(hi - acc) * UNIT);
+      while (row < rend) {
+        const int rem = rend - row;
+        const int tm = rem > 32 ? 64 : (rem > 16 ? 32 : 16);
+        f(tm, g, row, min(tm, rem));
+        row += tm;
+      }
+    }
+    acc += ug;
+  }
+}
+
+// For every column tile ct of the output: acc (TM x TN fragments) = rows(rowptr)[:, 0:Din] . B[0:Din, ct*TN : +TN],
+// then epi(col0, acc).  B element (k, n) at B[k*ldB + n].  ONE cp.async ring runs across all column tiles of the row
+// tile (no drain/refill between column tiles); `pre(col0)` is called when the first chunk of a column tile is issued
+// (used to prefetch epilogue operands).  All 256 threads must call.  Requires 16-byte aligned row starts.
+template <int TM, class Pre, class Epi>
+__device__ __forceinline__ void panel_gemm_all(PanelSmem<TM>& sm, const double* const* rowptr, int Din,
+                                               const double* __restrict__ B, int ldB, int Dout, Pre&& pre, Epi&& epi) {
   constexpr int MT = TM / 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+  double acc[MT][4][2];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const int nkc = (Din + KC - 1) / KC;
+  const int nct = (Dout + TN - 1) / TN;
+  const int total = nkc * nct;
 
-  auto load = [&](int stage, int kc) {
-    const int k0 = kc * KC;
-    for (int i = tid; i < TM * (KC / 2); i += NTHREADS) {
-      int r = i / (KC / 2), c2 = i % (KC / 2);
-      int k = k0 + c2 * 2;
-      const double* rp = rowptr[r];
-      int valid = rp ? max(0, min(2, Din - k)) : 0;
-      cp_async16(&sm.A[stage][r][c2 * 2], valid ? (const void*)(rp + k) : (const void*)B, valid * 8);
+  // ---- per-thread staging plan, hoisted out of the chunk loop (the address arithmetic used to cost ~4 integer
+  //      instructions per DMMA): each thread owns A_IT fixed 16-byte pieces of the A tile and B_IT of the B tile.
+  constexpr int A_IT = (TM * (KC / 2) + NTHREADS - 1) / NTHREADS;
+  constexpr int B_IT = KC * (TN / 2) / NTHREADS;
+  constexpr unsigned A_STAGE_BYTES = TM * A_STRIDE * 8, B_STAGE_BYTES = KC * B_STRIDE * 8;
+  const double* a_src[A_IT];      // source of this thread's j-th A piece (nullptr: row outside the tile)
+  unsigned a_dst[A_IT];           // shared address in stage 0 (bit 31: piece does not exist for this tile height)
+#pragma unroll
+  for (int j = 0; j < A_IT; ++j) {
+    int i = tid + j * NTHREADS;
+    int r = i / (KC / 2), c2 = i % (KC / 2);
+    bool on = i < TM * (KC / 2);
+    const double* rp = on ? rowptr[r] : nullptr;
+    a_src[j] = rp ? rp + c2 * 2 : nullptr;
+    a_dst[j] = (unsigned)__cvta_generic_to_shared(&sm.A[0][on ? r : 0][c2 * 2]) | (on ? 0u : 0x80000000u);
+  }
+  unsigned b_dst[B_IT];
+  int b_off[B_IT];
+#pragma unroll
+  for (int j = 0; j < B_IT; ++j) {
+    int i = tid + j * NTHREADS;
+    int kk = i / (TN / 2), c2 = (i % (TN / 2)) * 2;
+    b_dst[j] = (unsigned)__cvta_generic_to_shared(&sm.B[0][kk][c2]);
+    b_off[j] = kk * ldB + c2;
+  }
+  auto cp16 = [](unsigned dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+  };
+  auto cp16f = [](unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+  };
+  bool rows_full = true;          // every piece of this thread has a valid source row (CTA-uniform when nrows == TM)
+#pragma unroll
+  for (int j = 0; j < A_IT; ++j) rows_full = rows_full && ((a_dst[j] & 0x80000000u) || a_src[j] != nullptr);
+  rows_full = __syncthreads_and(rows_full);
+
+  auto load = [&](int it) {
+    const int stage = it % STAGES;
+    const int ct = it / nkc, kc = it - ct * nkc;
+    const int k0 = kc * KC, col0 = ct * TN;
+    if (kc == 0) pre(col0);
+    const bool full_k = k0 + KC <= Din;
+    const double* bcol = B + (long long)k0 * ldB + col0;
+    if (BM_FASTPATH && rows_full && full_k && col0 + TN <= Dout) {      // interior chunk: no predication at all
+#pragma unroll
+      for (int j = 0; j < A_IT; ++j)
+        if (!(a_dst[j] & 0x80000000u)) cp16f(a_dst[j] + stage * A_STAGE_BYTES, a_src[j] + k0);
+#pragma unroll
+      for (int j = 0; j < B_IT; ++j) cp16f(b_dst[j] + stage * B_STAGE_BYTES, bcol + b_off[j]);
+      return;
     }
-    for (int i = tid; i < KC * (TN / 2); i += NTHREADS) {
-      int kk = i / (TN / 2), c2 = i % (TN / 2);
-      int k = k0 + kk, col = col0 + c2 * 2;
-      int valid = (k < Din) ? max(0, min(2, Dout - col)) : 0;
-      cp_async16(&sm.B[stage][kk][c2 * 2], valid ? (const void*)(B + (long long)k * ldB + col) : (const void*)B,
-                 valid * 8);
+#pragma unroll
+    for (int j = 0; j < A_IT; ++j) {
+      if (a_dst[j] & 0x80000000u) continue;
+      const int c2 = ((tid + j * NTHREADS) % (KC / 2)) * 2;
+      int valid = a_src[j] ? (full_k ? 2 : max(0, min(2, Din - k0 - c2))) : 0;
+      cp16(a_dst[j] + stage * A_STAGE_BYTES, valid ? (const void*)(a_src[j] + k0) : (const void*)B, valid * 8);
+    }
+#pragma unroll
+    for (int j = 0; j < B_IT; ++j) {
+      const int i = tid + j * NTHREADS;
+      const int kk = i / (TN / 2), c2 = (i % (TN / 2)) * 2;
+      int valid = (full_k || k0 + kk < Din) ? max(0, min(2, Dout - col0 - c2)) : 0;
+      cp16(b_dst[j] + stage * B_STAGE_BYTES, valid ? (const void*)(bcol + b_off[j]) : (const void*)B, valid * 8);
     }
   };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nkc) load(s, s);
+    if (s < total) load(s);
     cp_async_commit();
   }
-  for (int kc = 0; kc < nkc; ++kc) {
+  int kc = 0, ct = 0;
+  for (int it = 0; it < total; ++it) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    int nx = kc + STAGES - 1;
-    if (nx < nkc) load(nx % STAGES, nx);
+    if (it + STAGES - 1 < total) load(it + STAGES - 1);
     cp_async_commit();
-    const int st = kc % STAGES;
+    const int st = it % STAGES;
 #pragma unroll
     for (int ks = 0; ks < KC; ks += 4) {
       double a[MT], b[4];
@@ -140,10 +241,20 @@ __device__ __forceinline__ void panel_gemm(PanelSmem<TM>& sm, const double* cons
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
+    if (++kc == nkc) {
+      epi(ct * TN, acc);
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      kc = 0; ++ct;
+    }
   }
   cp_async_wait<0>();
   __syncthreads();
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ------------------------------------------------------------------------------------------------
 // environment advance
@@ -158,16 +269,14 @@ struct AdvParams {
 };
 
 template <int TM>
-__global__ void __launch_bounds__(NTHREADS) k_env_advance(AdvParams P) {
+__device__ __forceinline__ void tile_env_advance(const AdvParams& P, unsigned char* smem_raw, int g, int row0, int nrows) {
   constexpr int MT = TM / 16;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   PanelSmem<TM>& sm = *reinterpret_cast<PanelSmem<TM>*>(smem_raw);
   __shared__ const double* rowptr[TM];
   __shared__ int rowid[TM];
   __shared__ double rscale[TM];
   __shared__ double rmax[TM][4];
-  int g, row0, nrows;
-  if (!locate_tile<TM>(P.gs, g, row0, nrows)) return;
+  __syncthreads();   // previous tile of this CTA is completely done with the shared arrays
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
   if (tid < TM) {
     int id = -1;
@@ -181,9 +290,7 @@ __global__ void __launch_bounds__(NTHREADS) k_env_advance(AdvParams P) {
   double tmax[MT];
 #pragma unroll
   for (int i = 0; i < MT; ++i) tmax[i] = 0.0;
-  for (int col0 = 0; col0 < P.Dout; col0 += TN) {
-    double acc[MT][4][2];
-    panel_gemm<TM>(sm, rowptr, P.Din, B, P.ldB, col0, P.Dout, acc);
+  panel_gemm_all<TM>(sm, rowptr, P.Din, B, P.ldB, P.Dout, [](int) {}, [&](int col0, double (&acc)[MT][4][2]) {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       int r = wm * (TM / 2) + mt * 8 + (lane >> 2);
@@ -196,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS) k_env_advance(AdvParams P) {
         int col = col0 + wn * 32 + nt * 8 + 2 * (lane & 3);
         double v0 = acc[mt][nt][0] * sc, v1 = acc[mt][nt][1] * sc;
         if (col + 1 < P.Dout) {
-          *reinterpret_cast<double2*>(orow + col) = make_double2(v0, v1);
+          if (!BM_NOEPI) *reinterpret_cast<double2*>(orow + col) = make_double2(v0, v1);
           tmax[mt] = fmax(tmax[mt], fmax(fabs(v0), fabs(v1)));
         } else if (col < P.Dout) {
           orow[col] = v0;
@@ -204,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS) k_env_advance(AdvParams P) {
         }
       }
     }
-  }
+  });
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     double m = tmax[mt];
@@ -221,6 +328,15 @@ __global__ void __launch_bounds__(NTHREADS) k_env_advance(AdvParams P) {
   }
 }
 
+__global__ void __launch_bounds__(NTHREADS, BM_MINBLOCKS) k_env_advance(AdvParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  for_each_tile(P.gs.goff, P.gs.ngroups, [&](int tm, int g, int row0, int nrows) {
+    if (tm == 64) tile_env_advance<64>(P, smem_raw, g, row0, nrows);
+    else if (tm == 32) tile_env_advance<32>(P, smem_raw, g, row0, nrows);
+    else tile_env_advance<16>(P, smem_raw, g, row0, nrows);
+  });
+}
+
 // ------------------------------------------------------------------------------------------------
 // psi_n = (L_n . A[p,q]) . R_n   -> psi, 1/psi, ln|psi| (true scale)
 // ------------------------------------------------------------------------------------------------
@@ -234,16 +350,14 @@ struct PsiParams {
 };
 
 template <int TM>
-__global__ void __launch_bounds__(NTHREADS) k_psi(PsiParams P) {
+__device__ __forceinline__ void tile_psi(const PsiParams& P, unsigned char* smem_raw, int g, int row0, int nrows) {
   constexpr int MT = TM / 16;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   PanelSmem<TM>& sm = *reinterpret_cast<PanelSmem<TM>*>(smem_raw);
   __shared__ const double* rowptr[TM];
   __shared__ const double* rrow[TM];
   __shared__ int rowid[TM];
   __shared__ double rsum[TM][4];
-  int g, row0, nrows;
-  if (!locate_tile<TM>(P.gs, g, row0, nrows)) return;
+  __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
   if (tid < TM) {
     int id = -1;
@@ -257,27 +371,36 @@ __global__ void __launch_bounds__(NTHREADS) k_psi(PsiParams P) {
   double part[MT];
 #pragma unroll
   for (int i = 0; i < MT; ++i) part[i] = 0.0;
-  for (int col0 = 0; col0 < P.Dr; col0 += TN) {
-    double acc[MT][4][2];
-    panel_gemm<TM>(sm, rowptr, P.Dl, B, P.ldA, col0, P.Dr, acc);
+  // R tile of a column pass: TM rows x 1 KB; prefetch it into L2 when the pass starts so the epilogue does not
+  // wait for HBM (ncu: the epilogue DFMAs collected as many stall samples as the DMMAs)
+  auto pre = [&](int col0) {
+    for (int i = tid; i < TM * 8; i += NTHREADS) {
+      const double* rr = rrow[i >> 3];
+      int col = col0 + (i & 7) * 16;
+      if (rr && col < P.Dr) prefetch_l2(rr + col);
+    }
+  };
+  panel_gemm_all<TM>(sm, rowptr, P.Dl, B, P.ldA, P.Dr, pre, [&](int col0, double (&acc)[MT][4][2]) {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       int r = wm * (TM / 2) + mt * 8 + (lane >> 2);
       const double* rr = rrow[r];
       if (!rr) continue;
+      double p0 = 0.0, p1 = 0.0;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         int col = col0 + wn * 32 + nt * 8 + 2 * (lane & 3);
         if (col + 1 < P.Dr) {
-          double2 rv = *reinterpret_cast<const double2*>(rr + col);
-          part[mt] = fma(acc[mt][nt][0], rv.x, part[mt]);
-          part[mt] = fma(acc[mt][nt][1], rv.y, part[mt]);
+          double2 rv = BM_NOEPI ? make_double2(1.0, 1.0) : *reinterpret_cast<const double2*>(rr + col);
+          p0 = fma(acc[mt][nt][0], rv.x, p0);
+          p1 = fma(acc[mt][nt][1], rv.y, p1);
         } else if (col < P.Dr) {
-          part[mt] = fma(acc[mt][nt][0], rr[col], part[mt]);
+          p0 = fma(acc[mt][nt][0], rr[col], p0);
         }
       }
+      part[mt] += p0 + p1;
     }
-  }
+  });
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     double s = part[mt];
@@ -295,6 +418,15 @@ __global__ void __launch_bounds__(NTHREADS) k_psi(PsiParams P) {
   }
 }
 
+__global__ void __launch_bounds__(NTHREADS, BM_MINBLOCKS) k_psi(PsiParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  for_each_tile(P.gs.goff, P.gs.ngroups, [&](int tm, int g, int row0, int nrows) {
+    if (tm == 64) tile_psi<64>(P, smem_raw, g, row0, nrows);
+    else if (tm == 32) tile_psi<32>(P, smem_raw, g, row0, nrows);
+    else tile_psi<16>(P, smem_raw, g, row0, nrows);
+  });
+}
+
 // ------------------------------------------------------------------------------------------------
 // S[p,q] = sum_{n in group(p,q)} L_n (x) R_n / psi_n   — split over samples, partial tiles to a workspace
 // ------------------------------------------------------------------------------------------------
@@ -303,9 +435,9 @@ constexpr int G_STRIDE = GT + 4;     // 132
 constexpr int GRAD_MAXCHUNK = 2048;  // samples per CTA (indices cached in shared memory)
 
 struct GradSmem {
-  double Ls[STAGES][KC][G_STRIDE];
-  double Rs[STAGES][KC][G_STRIDE];
-  double w[STAGES][KC];
+  double Ls[GSTAGES][KC][G_STRIDE];
+  double Rs[GSTAGES][KC][G_STRIDE];
+  double w[GSTAGES][KC];
   int idx[GRAD_MAXCHUNK];
 };
 
@@ -320,8 +452,9 @@ struct GradParams {
   int tiles_c;                     // number of column tiles
 };
 
-// grid = (max splits, tiles_a * tiles_c, ngroups)
-__global__ void __launch_bounds__(NTHREADS, 1) k_grad(GradParams P) {
+// grid = (max splits, tiles_a * tiles_c, ngroups); 16 warps (4 x 4), warp tile 32 x 32
+constexpr int GRAD_THREADS = 512;
+__global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GradSmem& sm = *reinterpret_cast<GradSmem*>(smem_raw);
   const int g = blockIdx.z;
@@ -332,19 +465,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_grad(GradParams P) {
   const int ta = blockIdx.y / P.tiles_c, tc = blockIdx.y % P.tiles_c;
   const int a0 = ta * GT, c0 = tc * GT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
-  for (int i = tid; i < cnt; i += NTHREADS) sm.idx[i] = P.perm ? P.perm[s0 + i] : s0 + i;
+  for (int i = tid; i < cnt; i += GRAD_THREADS) sm.idx[i] = P.perm ? P.perm[s0 + i] : s0 + i;
   __syncthreads();
 
-  double acc[8][4][2];
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int nkc = (cnt + KC - 1) / KC;
   auto load = [&](int stage, int kc) {
     const int k0 = kc * KC;
-    for (int i = tid; i < KC * (GT / 2); i += NTHREADS) {
+    for (int i = tid; i < KC * (GT / 2); i += GRAD_THREADS) {
       int kk = i / (GT / 2), c2 = i % (GT / 2);
       int k = k0 + kk;
       bool rv = k < cnt;
@@ -362,27 +495,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_grad(GradParams P) {
     }
   };
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
+  for (int s = 0; s < GSTAGES - 1; ++s) {
     if (s < nkc) load(s, s);
     cp_async_commit();
   }
   for (int kc = 0; kc < nkc; ++kc) {
-    cp_async_wait<STAGES - 2>();
+    cp_async_wait<GSTAGES - 2>();
     __syncthreads();
-    int nx = kc + STAGES - 1;
-    if (nx < nkc) load(nx % STAGES, nx);
+    int nx = kc + GSTAGES - 1;
+    if (nx < nkc) load(nx % GSTAGES, nx);
     cp_async_commit();
-    const int st = kc % STAGES;
+    const int st = kc % GSTAGES;
 #pragma unroll
     for (int ks = 0; ks < KC; ks += 4) {
-      double a[8], b[4];
+      double a[4], b[4];
       const double wv = sm.w[st][ks + (lane & 3)];
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) a[mt] = sm.Ls[st][ks + (lane & 3)][wm * 64 + mt * 8 + (lane >> 2)];
+      for (int mt = 0; mt < 4; ++mt) a[mt] = sm.Ls[st][ks + (lane & 3)][wm * 32 + mt * 8 + (lane >> 2)];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) b[nt] = sm.Rs[st][ks + (lane & 3)][wn * 32 + nt * 8 + (lane >> 2)] * wv;
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt)
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
@@ -392,8 +525,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_grad(GradParams P) {
   const int p = g / P.d, q = g % P.d;
   double* out = P.ws + (long long)blockIdx.x * P.ws_stride + (long long)p * P.Dl * P.ldA + (long long)q * P.ldRpad;
 #pragma unroll
-  for (int mt = 0; mt < 8; ++mt) {
-    int a = a0 + wm * 64 + mt * 8 + (lane >> 2);
+  for (int mt = 0; mt < 4; ++mt) {
+    int a = a0 + wm * 32 + mt * 8 + (lane >> 2);
     if (a >= P.Dl) continue;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -435,22 +568,29 @@ struct SampleParams {
   const double* U;
   uint8_t* pix_out;
   int n; int strict; int pix_first; int both_norm;
+  const int* goff;     // {0, n}
+};
+
+struct SampleShared {     // one copy for all tile heights (keeps the kernel at 2 CTAs / SM)
+  const double* rowptr[64];
+  int rowid[64];
+  double rscale[64];
+  double red[64][4];
+  double n1s[64], m1s[64], n2s[64], m2s[64];
+  int accs[64];
 };
 
 template <int TM>
-__global__ void __launch_bounds__(NTHREADS) k_sample_step(SampleParams P) {
+__device__ __forceinline__ void tile_sample(const SampleParams& P, unsigned char* smem_raw, SampleShared& sh, int row0, int nrows) {
   constexpr int MT = TM / 16;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   PanelSmem<TM>& sm = *reinterpret_cast<PanelSmem<TM>*>(smem_raw);
-  __shared__ const double* rowptr[TM];
-  __shared__ int rowid[TM];
-  __shared__ double rscale[TM];
-  __shared__ double red[TM][4];
-  __shared__ double n1s[TM], m1s[TM], n2s[TM], m2s[TM];
-  __shared__ int accs[TM];
-  const int row0 = blockIdx.x * TM;
-  if (row0 >= P.n) return;
-  const int nrows = min(TM, P.n - row0);
+  const double** rowptr = sh.rowptr;
+  int* rowid = sh.rowid;
+  double* rscale = sh.rscale;
+  double (*red)[4] = sh.red;
+  double *n1s = sh.n1s, *m1s = sh.m1s, *n2s = sh.n2s, *m2s = sh.m2s;
+  int* accs = sh.accs;
+  __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
   if (tid < TM) {
     int id = tid < nrows ? row0 + tid : -1;
@@ -467,9 +607,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sample_step(SampleParams P) {
     double nn[MT], mm[MT];
 #pragma unroll
     for (int i = 0; i < MT; ++i) nn[i] = mm[i] = 0.0;
-    for (int col0 = 0; col0 < P.Dout; col0 += TN) {
-      double acc[MT][4][2];
-      panel_gemm<TM>(sm, rowptr, P.Din, B, P.ldB, col0, P.Dout, acc);
+    panel_gemm_all<TM>(sm, rowptr, P.Din, B, P.ldB, P.Dout, [](int) {}, [&](int col0, double (&acc)[MT][4][2]) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         int r = wm * (TM / 2) + mt * 8 + (lane >> 2);
@@ -493,7 +631,7 @@ __global__ void __launch_bounds__(NTHREADS) k_sample_step(SampleParams P) {
           }
         }
       }
-    }
+    });
     // norms
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -538,6 +676,16 @@ __global__ void __launch_bounds__(NTHREADS) k_sample_step(SampleParams P) {
     P.e_out[id] = frexp_exp(a ? m1s[tid] : m2s[tid]);
     P.pix_out[id] = (uint8_t)(a ? P.pix_first : 1 - P.pix_first);
   }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2) k_sample_step(SampleParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ SampleShared sh;
+  for_each_tile(P.goff, 1, [&](int tm, int g, int row0, int nrows) {
+    if (tm == 64) tile_sample<64>(P, smem_raw, sh, row0, nrows);
+    else if (tm == 32) tile_sample<32>(P, smem_raw, sh, row0, nrows);
+    else tile_sample<16>(P, smem_raw, sh, row0, nrows);
+  });
 }
 
 // ------------------------------------------------------------------------------------------------
