@@ -32,12 +32,12 @@ def canonize(mps, centre):
         dl, dr, d = m[k].shape
         q, r = np.linalg.qr(m[k].transpose(0, 2, 1).reshape(dl * d, dr))
         m[k] = q.reshape(dl, d, -1).transpose(0, 2, 1)
-        m[k + 1] = np.einsum('ab,bcp->acp', r, m[k + 1])
+        m[k + 1] = np.tensordot(r, m[k + 1], axes=([1], [0]))
     for k in range(L - 1, centre, -1):
         dl, dr, d = m[k].shape
         q, r = np.linalg.qr(m[k].reshape(dl, dr * d).T)
         m[k] = q.T.reshape(-1, dr, d)
-        m[k - 1] = np.einsum('abp,bc->acp', m[k - 1], r.T)
+        m[k - 1] = np.tensordot(m[k - 1], r.T, axes=([1], [0])).transpose(0, 2, 1)
     return squeeze_chain(m)
 
 

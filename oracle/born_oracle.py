@@ -176,11 +176,11 @@ def canonize(mps, centre):
     for k in range(0, centre):
         q, r = _qr_left(m[k])
         m[k] = q
-        m[k + 1] = np.einsum('ab,bcp->acp', r, m[k + 1])
+        m[k + 1] = np.tensordot(r, m[k + 1], axes=([1], [0]))
     for k in range(L - 1, centre, -1):
         lf, q = _lq_right(m[k])
         m[k] = q
-        m[k - 1] = np.einsum('abp,bc->acp', m[k - 1], lf)
+        m[k - 1] = np.tensordot(m[k - 1], lf, axes=([1], [0])).transpose(0, 2, 1)
     return from_site3(m)
 
 
@@ -360,7 +360,7 @@ class EnvCache:
 # ----------------------------------------------------------------------------------------------
 def merge(mps, k):
     """A = M_k . M_{k+1}, (Dl,d,Dr,d)  (TNutils.py:1388, :1526)."""
-    return np.einsum('abp,bcq->apcq', site3(mps, k), site3(mps, k + 1))
+    return np.tensordot(site3(mps, k), site3(mps, k + 1), axes=([1], [0]))    # (a,p,c,q), BLAS-backed
 
 
 def psi_and_grad(A, lv, rv, pk, pk1):
