@@ -664,7 +664,7 @@ static int run_svd_gesvdj(bm_ctx* c, int mA, int nA) {
 //   Outputs: isometry (p x r) and absorbed factor (q x chi) in c->U / c->V, singular values in c->h_s, chi.
 static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond, double cutoff, int* chi_out, double* trunc_out) {
   Timer t_(c, 5);
-  constexpr double TAU = 1e-5;
+  constexpr double TAU = 1e-7;   // level-0 values down to 3e-4 s_0: rel. error <= eps*n/(2 tau) ~ 2.5e-7
   const int p = going_right ? mA : nA, q = going_right ? nA : mA;
   double* iso = going_right ? c->U : c->V;
   double* absb = going_right ? c->V : c->U;
