@@ -187,7 +187,7 @@ def run_ours(args):
     shard = imgs[rank * per:min(N, (rank + 1) * per)]
     start = k0 - warm
     mps = mpslib.random_mps(L, D, rng=np.random.default_rng(11), centre=start)
-    eng = BornEngine(L, D, device=local, svd=args.svd)
+    eng = BornEngine(L, D, device=local, svd=args.svd, precision=args.precision)
     eng.set_data(shard, n_total=N)
     eng.set_mps(mps)
     eng.env_build(start)
@@ -294,7 +294,7 @@ def run_ours(args):
         line = {
             'metric': 'sample_site_updates_per_s_two_site_sweep', 'value': value, 'unit': 'sample·site updates/s',
             'n_gpus': world, 'steps': steps, 'warmup': warm, 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64' if args.precision == 'fp64' else 'f64 (gradient accumulation: tf32 operands, f32 TMEM accumulators)', 'data': 'synthetic',
             'config': workload_config(args.workload, world),
             'e2e': {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps,
                     'd2h_bytes_per_step': d2h // steps},
@@ -389,6 +389,8 @@ def main():
     ap.add_argument('--samples', type=int, default=0)
     ap.add_argument('--svd', default='gram', choices=['gram', 'gesvdj'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32'],
+                    help="fp64 (default, 1e-6 parity) or tf32 (gradient accumulation on tcgen05/TMEM, 1e-3 parity)")
     ap.add_argument('--sampler-bond', type=int, default=500)
     args = ap.parse_args()
     if args.workload == 'c4':

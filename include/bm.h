@@ -50,6 +50,9 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
 int bm_destroy(bm_ctx* ctx);
 const char* bm_last_error(bm_ctx* ctx);
 int bm_set_svd(bm_ctx* ctx, int method);
+/* grad_tf32 = 1: accumulate S = sum psi'/psi with tcgen05.mma.kind::tf32 into TMEM (1e-3 parity class; bonds <= 256,
+ * larger bonds fall back to the FP64 DMMA kernel).  psi, environments, update and split stay FP64. */
+int bm_set_precision(bm_ctx* ctx, int grad_tf32);
 
 /* a1: stater/tens_picture (TNutils.py:446-455), torchized_imgs (:1011-1027).  Uploads the training
  * images, embeds them, builds the per-bond pixel-pair groupings and allocates the environment stack

@@ -19,6 +19,7 @@ _SIGS = [
     ('bm_destroy', C.c_int, [_P]),
     ('bm_last_error', C.c_char_p, [_P]),
     ('bm_set_svd', C.c_int, [_P, C.c_int]),
+    ('bm_set_precision', C.c_int, [_P, C.c_int]),
     ('bm_set_data', C.c_int, [_P, _P, C.c_int]),
     ('bm_set_site', C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int]),
     ('bm_get_site', C.c_int, [_P, C.c_int, _P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

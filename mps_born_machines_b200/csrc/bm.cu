@@ -45,6 +45,8 @@ struct bm_ctx {
   cusolverDnHandle_t cusolver = nullptr;
   gesvdjInfo_t gesvdj = nullptr;
   int svd_method = BM_SVD_GESVDJ;
+  int grad_tf32 = 0;            // 1: gradient accumulation on tcgen05 (TF32 operands, FP32 TMEM accumulators)
+  int* tf_status = nullptr;     // device flag raised by a bounded mbarrier wait that timed out
   long long launches = 0;
   int n_sm = 148, panel_ctas = 296;
 
@@ -164,6 +166,7 @@ int set_func_attrs(bm_ctx* c) {
   CU(cudaFuncSetAttribute(k_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
   CU(cudaFuncSetAttribute(k_sample_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
   CU(cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradSmem)));
+  CU(cudaFuncSetAttribute(k_grad_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradTf32Smem)));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, c->device));
   c->n_sm = prop.multiProcessorCount;
@@ -338,7 +341,8 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
   const size_t mA = (size_t)c->d * c->Dcap, ldA = (size_t)c->d * c->ldcap;
   DALLOC(c->Aint, mA * ldA); DALLOC(c->A2, mA * ldA); DALLOC(c->G, mA * ldA + 2);
   DALLOC(c->W, mA * mA); DALLOC(c->U, mA * mA); DALLOC(c->V, mA * mA); DALLOC(c->Ssv, mA); DALLOC(c->sgn, mA);
-  DALLOC(c->info, 1); DALLOC(c->iscal, 4);
+  DALLOC(c->info, 1); DALLOC(c->iscal, 4); DALLOC(c->tf_status, 1);
+  CU(cudaMemsetAsync(c->tf_status, 0, sizeof(int), c->stream));
   DALLOC(c->Gq, mA * mA); DALLOC(c->Yb[0], mA * mA); DALLOC(c->Yb[1], mA * mA); DALLOC(c->Tb[0], mA * mA); DALLOC(c->Tb[1], mA * mA);
   DALLOC(c->Tmp, mA * mA); DALLOC(c->lam, mA);
   CU(cudaMallocHost((void**)&c->h_lam, (mA + 2) * sizeof(double)));
@@ -354,7 +358,7 @@ int bm_destroy(bm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -382,6 +386,12 @@ int bm_set_timing(bm_ctx* c, int on) {
 int bm_get_timing(bm_ctx* c, double* ms8, long long* n8) {
   if (!c || !ms8 || !n8) return BM_EINVAL;
   for (int i = 0; i < 8; ++i) { ms8[i] = c->t_ms[i]; n8[i] = c->t_n[i]; }
+  return BM_OK;
+}
+
+int bm_set_precision(bm_ctx* c, int grad_tf32) {
+  if (!c) return BM_EINVAL;
+  c->grad_tf32 = grad_tf32 ? 1 : 0;
   return BM_OK;
 }
 
@@ -610,7 +620,8 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
   }
   // ---- gradient accumulation
   {
-    const int tiles_a = (Dl + GT - 1) / GT, tiles_c = (Dr + GT - 1) / GT;
+    const bool tf32 = c->grad_tf32 && Dl <= TF_TILE && Dr <= TF_TILE;
+    const int tiles_a = tf32 ? 1 : (Dl + GT - 1) / GT, tiles_c = tf32 ? 1 : (Dr + GT - 1) / GT;
     int maxg = 0;
     for (int g = 0; g < G; ++g) maxg = std::max(maxg, h_goff[g + 1] - h_goff[g]);
     // samples per split: minimise the makespan  ceil(items / #SM) * kchunk  over multiples of 16
@@ -636,7 +647,11 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     P.winv = c->winv; P.perm = perm; P.goff = goff; P.ngroups = G; P.d = d;
     P.kchunk = kchunk; P.ws = c->ws; P.ws_stride = (long long)rows * ldA; P.ldA = ldA; P.ldRpad = ldr; P.tiles_c = tiles_c;
     dim3 grid(std::max(nsplit, 1), tiles_a * tiles_c, G);
-    { Timer t_(c, 2); k_grad<<<grid, GRAD_THREADS, sizeof(GradSmem), c->stream>>>(P); }
+    {
+      Timer t_(c, 2);
+      if (tf32) k_grad_tf32<<<grid, TF_THREADS, sizeof(GradTf32Smem), c->stream>>>(P, c->tf_status);
+      else k_grad<<<grid, GRAD_THREADS, sizeof(GradSmem), c->stream>>>(P);
+    }
     { Timer t_(c, 3); k_grad_reduce<<<148 * 4, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, S_dev); }
     k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, S_dev + (size_t)rows * ldA);
     c->launches += 3;
@@ -753,7 +768,9 @@ int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, do
 
   // zero-psi check before touching anything (TNutils.py:1244-1254)
   CU(cudaMemcpyAsync(c->h_scal, S_dev + (size_t)rows * ldA, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_iscal + 3, c->tf_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->h_iscal[3] != 0) return fail(c, BM_ECUDA, "k_grad_tf32: mbarrier wait timed out (tcgen05 pipeline)");
   const double sumln = c->h_scal[0], nzero = c->h_scal[1];
   if (nzero > 0) {
     if (scalars_host) { std::memset(scalars_host, 0, 8 * sizeof(double)); scalars_host[1] = sumln; scalars_host[2] = nzero; }

@@ -538,6 +538,173 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TF32 gradient kernel (opt-in, 1e-3 parity): S[p,q] = sum_n L_n (x) R_n / psi_n  on the 5th-gen tensor cores.
+//   tcgen05.mma.cta_group::1.kind::tf32, M = 128 (rows a), N = Dr rounded to 16 (<= 256), K = 8 samples per MMA;
+//   the whole (Dl x Dr) block of one pixel-pair group is accumulated in TMEM (2 x 256 columns x 128 lanes fp32).
+//   Operands are converted FP64 -> TF32 while being staged, and written TRANSPOSED into the canonical K-major
+//   no-swizzle layout (core matrix = 8 rows x 16 B): elem(a, n) -> (a%8)*16 B + (n/4)*LBO + (a/8)*SBO + (n%4)*4 B,
+//   SBO = 128 B, LBO = 32 * 128 B  (MN-major TF32 operands would need the SW128_32B swizzle; K-major avoids it).
+//   One elected thread issues the MMAs; tcgen05.commit releases a stage through an mbarrier.
+//   The partial block is written to the same FP64 split workspace as k_grad, so k_grad_reduce is shared.
+// ------------------------------------------------------------------------------------------------
+constexpr int TF_KS = 32;                         // samples per stage
+constexpr int TF_STAGES = 3;
+constexpr int TF_TILE = 256;                      // max Dl, Dr
+constexpr int TF_LBO = (TF_TILE / 8) * 128;       // 4096 B between 4-sample chunks
+constexpr int TF_SBO = 128;                       // between groups of 8 rows
+constexpr int TF_OP_BYTES = (TF_KS / 4) * TF_LBO; // 32 KB per operand per stage
+constexpr int TF_THREADS = 256;
+
+struct GradTf32Smem {
+  unsigned char L[TF_STAGES][TF_OP_BYTES];
+  unsigned char R[TF_STAGES][TF_OP_BYTES];
+  int idx[GRAD_MAXCHUNK];
+  double w[GRAD_MAXCHUNK];
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version 1 (sm_100); no swizzle, base offset 0
+  return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {   // D = F32, A = B = TF32, both K-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must never hang the GPU box; status[0] is raised instead
+__device__ __forceinline__ bool mbar_wait_bounded(unsigned bar, unsigned parity, int* status) {
+  for (int i = 0; i < (1 << 24); ++i) if (mbar_try_wait(bar, parity)) return true;
+  if (status) atomicExch(status, 1);
+  return false;
+}
+
+// grid = (max splits, 1, ngroups); requires Dl, Dr <= 256
+__global__ void __launch_bounds__(TF_THREADS, 1) k_grad_tf32(GradParams P, int* status) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  GradTf32Smem& sm = *reinterpret_cast<GradTf32Smem*>(smem_raw);
+  __shared__ __align__(8) unsigned long long bars[TF_STAGES + 1];
+  __shared__ uint32_t tmem_base_s;
+  const int g = blockIdx.z;
+  const int gbeg = P.goff[g], gend = P.goff[g + 1];
+  const int s0 = gbeg + blockIdx.x * P.kchunk;
+  if (s0 >= gend) return;
+  const int cnt = min(P.kchunk, gend - s0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mtiles = (P.Dl + 127) / 128;
+  const int npad = (P.Dr + 15) & ~15;
+
+  for (int i = tid; i < cnt; i += TF_THREADS) {
+    int id = P.perm ? P.perm[s0 + i] : s0 + i;
+    sm.idx[i] = id;
+    sm.w[i] = P.winv[id];
+  }
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&bars[0]);
+  if (tid == 0) {
+    for (int s = 0; s <= TF_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8 * s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(&tmem_base_s);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = umma_idesc_tf32(128, npad);
+
+  // staging: thread owns column (a or c) = tid, for every 4-sample chunk of the stage
+  const int nblk = (cnt + TF_KS - 1) / TF_KS;
+  bool alive = true;
+  for (int blk = 0; blk < nblk && alive; ++blk) {
+    const int st = blk % TF_STAGES;
+    if (blk >= TF_STAGES) alive = mbar_wait_bounded(bar0 + 8 * st, ((blk / TF_STAGES) - 1) & 1, status);   // MMAs that read this stage are done
+    const int n0 = blk * TF_KS;
+    unsigned char* dL = sm.L[st] + (tid & 7) * 16 + (tid >> 3) * TF_SBO;
+    unsigned char* dR = sm.R[st] + (tid & 7) * 16 + (tid >> 3) * TF_SBO;
+    // 16 samples at a time: issue all 32 global loads first (64 KB in flight per SM), then convert and store
+#pragma unroll
+    for (int half = 0; half < TF_KS / 16; ++half) {
+      double lv[16], rv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + half * 16 + j;
+        lv[j] = 0.0; rv[j] = 0.0;
+        if (n < cnt) {
+          const long long id = sm.idx[n];
+          if (tid < P.Dl) lv[j] = P.Lenv[id * P.ldL + tid];
+          if (tid < P.Dr) rv[j] = P.Renv[id * P.ldR + tid];
+        }
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int ch = half * 4 + c4;
+        const int nb = n0 + half * 16 + c4 * 4;
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = (nb + j < cnt) ? (float)(rv[c4 * 4 + j] * sm.w[nb + j]) : 0.f;
+        *reinterpret_cast<float4*>(dL + ch * TF_LBO) = make_float4((float)lv[c4 * 4], (float)lv[c4 * 4 + 1], (float)lv[c4 * 4 + 2], (float)lv[c4 * 4 + 3]);
+        *reinterpret_cast<float4*>(dR + ch * TF_LBO) = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> async proxy (UMMA reads)
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aL = (uint32_t)__cvta_generic_to_shared(sm.L[st]), aR = (uint32_t)__cvta_generic_to_shared(sm.R[st]);
+#pragma unroll
+      for (int ks = 0; ks < TF_KS / 8; ++ks) {
+        const uint64_t db = umma_desc(aR + ks * 2 * TF_LBO, TF_LBO, TF_SBO);
+        for (int mt = 0; mt < mtiles; ++mt) {
+          const uint64_t da = umma_desc(aL + ks * 2 * TF_LBO + mt * 16 * TF_SBO, TF_LBO, TF_SBO);
+          const uint32_t acc = (blk > 0 || ks > 0) ? 1u : 0u;
+          asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                       :: "r"(tmem + (uint32_t)(mt * 256)), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar0 + 8 * st) : "memory");
+      if (blk == nblk - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar0 + 8 * TF_STAGES) : "memory");
+    }
+  }
+  // ---- epilogue: all MMAs done -> TMEM -> FP64 partial block in the split workspace
+  if (alive) alive = mbar_wait_bounded(bar0 + 8 * TF_STAGES, 0, status);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (alive) {
+    const int p = g / P.d, q = g % P.d;
+    double* out = P.ws + (long long)blockIdx.x * P.ws_stride + (long long)p * P.Dl * P.ldA + (long long)q * P.ldRpad;
+    const int mt = warp >> 2;                       // warps 0-3: rows 0..127, warps 4-7: rows 128..255
+    const int a = mt * 128 + (warp & 3) * 32 + lane;
+    if (mt < mtiles) {
+      for (int c0 = 0; c0 < npad; c0 += 8) {
+        uint32_t r[8];
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 256 + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a < P.Dl) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < P.Dr) out[(long long)a * P.ldA + c0 + j] = (double)__uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
 // S[e] = sum over the splits of e's group, in split order (deterministic).  Pads are written as 0.
 __global__ void k_grad_reduce(const double* __restrict__ ws, long long ws_stride, const int* __restrict__ goff,
                               int kchunk, int d, int Dl, int Dr, int ldA, int ldRpad, double* __restrict__ S) {

@@ -29,7 +29,7 @@ def sweep_schedule(L):
 
 
 class BornEngine:
-    def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gram', dist_group=None):
+    def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gram', dist_group=None, precision='fp64'):
         if not torch.cuda.is_available():
             raise RuntimeError('BornEngine needs a CUDA device (sm_100a); there is no CPU fallback')
         self.L, self.d, self.Dcap = int(n_sites), int(phys_dim), int(max_bond)
@@ -41,6 +41,10 @@ class BornEngine:
         code = self._lib.bm_create(C.byref(self._ctx), self.device, self.L, self.d, self.Dcap, C.c_void_p(stream))
         check(self._ctx, code)
         check(self._ctx, self._lib.bm_set_svd(self._ctx, SVD[svd]))
+        if precision not in ('fp64', 'tf32'):
+            raise ValueError("precision must be 'fp64' or 'tf32'")
+        check(self._ctx, self._lib.bm_set_precision(self._ctx, 1 if precision == 'tf32' else 0))
+        self.precision = precision
         ld = (self.Dcap + 1) & ~1
         self._S = torch.zeros(self.d * self.Dcap * self.d * ld + 2, dtype=torch.float64, device=f'cuda:{self.device}')
         self.N = 0

@@ -333,3 +333,41 @@ def test_config2_mid_chain_steps(bm):
         np.testing.assert_allclose(out['sum_logpsi'], sum_log_ref, rtol=RTOL)
         np.testing.assert_allclose(out['Z'], ref['Z'], rtol=RTOL)
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TF32 family (tcgen05 + TMEM gradient accumulation): 1e-3 parity class
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('L,D,N,seed', [(10, 8, 300, 101), (8, 24, 1000, 102), (6, 5, 77, 103)])
+def test_tf32_gradient_matches_oracle(bm, L, D, N, seed):
+    mps, imgs = make_problem(L, D, N, seed)
+    phys = o.embed(imgs)
+    d = 2
+    eng = bm.BornEngine(L, max(o.bond_sizes(mps)) * d, precision='tf32')
+    eng.set_mps(mps); eng.set_data(imgs)
+    cache = o.EnvCache(mps, phys, 'pow2')
+    for k in (0, 1, L // 2, L - 2):
+        S = eng.step_grad(k)
+        A = o.merge(mps, k)
+        _, S_ref = o.psi_and_grad(A, cache.lenv[k], cache.renv[k + 2], phys[:, k], phys[:, k + 1])
+        S_eng = eng.grad_to_ref(k, S)
+        # TF32 operands (10-bit mantissa), FP32 accumulation: error relative to the scale of the sum of magnitudes
+        scale = np.abs(S_ref).max()
+        assert np.abs(S_eng - S_ref).max() < 3e-3 * scale, (k, np.abs(S_eng - S_ref).max() / scale)
+    eng.close()
+
+
+def test_tf32_training_nll_within_1e3(bm):
+    """TF32 path: per-epoch NLL within 1e-3 relative of the FP64 oracle (gauge-invariant l2 rule)."""
+    L, N = 12, 200
+    mps0, imgs = make_problem(L, 3, N, 133)
+    mps_o = [t.copy() for t in mps0]
+    cost_o, _ = o.learning_epoch_cached(mps_o, imgs, 3, 0.02, renorm='l2', max_bond=8, cutoff=1e-8)
+    eng = bm.BornEngine(L, 8, precision='tf32')
+    eng.set_mps(mps0); eng.set_data(imgs)
+    cost = []
+    for _ in range(3):
+        eng.epoch(0.02, 'l2', max_bond=8, cutoff=1e-8)
+        cost.append(eng.nll(imgs, 0))
+    np.testing.assert_allclose(cost, cost_o, rtol=1e-3)
+    eng.close()

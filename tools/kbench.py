@@ -11,6 +11,8 @@ ap.add_argument('--d', type=int, default=256)
 ap.add_argument('--sites', type=int, default=24)
 ap.add_argument('--steps', type=int, default=6)
 ap.add_argument('--svd', default='gram')
+ap.add_argument('--precision', default='fp64')
+ap.add_argument('--check', action='store_true')
 a = ap.parse_args()
 L, D, N = a.sites, a.d, a.n
 imgs = mpslib.synthetic_images(N, L)
@@ -23,9 +25,14 @@ for k in range(L):      # bonds: min(D, 2^k, 2^(L-k)) would be tiny at the ends;
     mats.append(rng.standard_normal((dl, dr, 2)) / np.sqrt(dr * 2))
 mps = mpslib.canonize(mpslib.squeeze_chain(mats), k0)
 mps[k0] = mps[k0] / np.linalg.norm(mps[k0])
-eng = BornEngine(L, D, svd=a.svd)
+eng = BornEngine(L, D, svd=a.svd, precision=a.precision)
 eng.set_data(imgs); eng.set_mps(mps); eng.env_build(k0)
 k = k0
+if a.check:
+    ref = BornEngine(L, D, svd=a.svd, precision='fp64'); ref.set_data(imgs); ref.set_mps(mps); ref.env_build(k0)
+    S1 = eng.grad_to_ref(k0, eng.step_grad(k0)); S0 = ref.grad_to_ref(k0, ref.step_grad(k0))
+    print(json.dumps({'check': 'tf32 vs fp64 gradient at D=%d N=%d' % (D, N), 'max_abs_diff_over_max': float(np.abs(S1 - S0).max() / np.abs(S0).max()), 'rel_fro': float(np.linalg.norm(S1 - S0) / np.linalg.norm(S0))}))
+    ref.close()
 for _ in range(2):
     eng.step(k, 1e-3, True, renorm='l2', max_bond=D); k += 1
 eng.set_timing(True)
