@@ -34,6 +34,9 @@ constexpr int NTHREADS = 256;   // 8 warps arranged 2 (rows) x 4 (cols)
 #ifndef BM_MINBLOCKS
 #define BM_MINBLOCKS 2
 #endif
+#ifndef BM_PSI_BATCH
+#define BM_PSI_BATCH 1
+#endif
 #ifndef BM_NOEPI
 #define BM_NOEPI 0      // tuning only: skip epilogue memory traffic
 #endif
@@ -381,15 +384,27 @@ __device__ __forceinline__ void tile_psi(const PsiParams& P, unsigned char* smem
     }
   };
   panel_gemm_all<TM>(sm, rowptr, P.Dl, B, P.ldA, P.Dr, pre, [&](int col0, double (&acc)[MT][4][2]) {
+    const bool interior = col0 + TN <= P.Dr;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       int r = wm * (TM / 2) + mt * 8 + (lane >> 2);
       const double* rr = rrow[r];
       if (!rr) continue;
+      const int cb = col0 + wn * 32 + 2 * (lane & 3);
+      if (BM_PSI_BATCH && interior) {
+        double2 rv[4];                       // all four loads of this row in flight before the first FMA
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) rv[nt] = BM_NOEPI ? make_double2(1.0, 1.0) : *reinterpret_cast<const double2*>(rr + cb + nt * 8);
+        double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { p0 = fma(acc[mt][nt][0], rv[nt].x, p0); p1 = fma(acc[mt][nt][1], rv[nt].y, p1); }
+        part[mt] += p0 + p1;
+        continue;
+      }
       double p0 = 0.0, p1 = 0.0;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        int col = col0 + wn * 32 + nt * 8 + 2 * (lane & 3);
+        int col = cb + nt * 8;
         if (col + 1 < P.Dr) {
           double2 rv = BM_NOEPI ? make_double2(1.0, 1.0) : *reinterpret_cast<const double2*>(rr + col);
           p0 = fma(acc[mt][nt][0], rv.x, p0);
