@@ -125,6 +125,12 @@ int bm_last_logpsi(bm_ctx* ctx, double* lnabs_host);
 int bm_sample(bm_ctx* ctx, int n, int rule, int start_site, const double* U_host, uint64_t seed,
               const uint8_t* prefix_pixels_host, uint8_t* out_host);
 
+/* a11, general masks: reconstruct (TNutils.py:2053-2116) of ONE image whose unknown pixels (255) may sit anywhere.
+ * The known pixels are contracted, the unknown ones are sampled left to right from their exact conditionals (right
+ * environments E_j = sum_x M_j[x] E_{j+1} M_j[x]^T), pixel 0 first with `u < P` like generate_sample (:1950).
+ * u_host: one uniform per unknown pixel, in site order. */
+int bm_reconstruct_one(bm_ctx* ctx, const uint8_t* pixels_host, const double* u_host, int n_unknown, uint8_t* out_host);
+
 /* Device-resident variants for benchmarking (no host traffic): uniforms generated on device, output
  * left on device.  Returns elapsed device milliseconds of the sampling loop in *ms. */
 int bm_sample_device(bm_ctx* ctx, int n, int rule, uint64_t seed, float* ms);

@@ -5,7 +5,7 @@ Same names, argument meaning and error behaviour as `/root/reference/TNutils.py`
     initialize_mps :386      stater :446 / tens_picture :452        left_right_cache :457
     sequential_update :504   computepsi :627                        computeNLL :872 / computeNLL_cached :892
     learning_step_cached :1510   learning_epoch_cached :1570        compress / compress_copy / compress2 :930-993
-    generate_samples :1829   generate_sample :1874                  reconstruct :2053 (known-prefix masks)
+    generate_samples :1829   generate_sample :1874                  reconstruct :2053 (any mask)
     bars_n_stripes :2243     partial_removal_img :211               mps_lr :76      zero / one :1822-1827
 
 quimb is not available, so `Tensor` / `MPS` below are minimal duck types exposing what the notebooks touch
@@ -606,15 +606,24 @@ def generate_sample(mps):
 
 
 def reconstruct(mps, corr_img):
-    """TNutils.py:2053-2116 for images whose unknown pixels (-1) form a suffix (partial_removal_img axis=0,
-    half=0): the known prefix is contracted on the device and the remaining sites are sampled conditionally."""
+    """TNutils.py:2053-2116.  Known-prefix masks (partial_removal_img axis=0, half=0) take the batched sampler path
+    (prefix contracted on the device, remaining sites sampled from the right-canonical tail); any other mask takes
+    the general path (right-environment matrices, bm_reconstruct_one)."""
     corr_img = np.asarray(corr_img)
     unknown = np.nonzero(corr_img == -1)[0]
     if unknown.size == 0:
         return corr_img.copy()
     start = int(unknown[0])
     if not np.all(corr_img[start:] == -1):
-        raise NotImplementedError('only known-prefix masks are supported by the device path (SURVEY.md 8f-3)')
+        # general mask: exact conditionals from right-environment matrices on the device (one image at a time, like
+        # the reference); one np.random.rand() per unknown pixel in site order, as generate_sample draws them
+        rec = mps.copy().normalize()
+        u = np.array([np.random.rand() for _ in range(unknown.size)])
+        eng = BornEngine(len(rec.tensors), max(rec.max_bond(), 2))
+        eng.set_mps(rec.arrays())
+        out = eng.reconstruct_one(corr_img, u)
+        eng.close()
+        return out.astype(corr_img.dtype)
     rec = mps.copy().normalize().right_canonize()
     L = len(rec.tensors)
     U = np.array([[np.random.rand()] for _ in range(L - start)])

@@ -85,6 +85,9 @@ struct bm_ctx {
   int last_kchunk = 0;
 
   Chain chain;
+  // general-mask reconstruction: right-environment matrices E_j (row-major Dcap x Dcap each), vectors, counters
+  double* recE = nullptr; double* recT = nullptr; double* recV[2] = {nullptr, nullptr}; double* recU = nullptr;
+  uint8_t* recPix = nullptr; int* recCount = nullptr;
 
   // optional per-kernel timing (bm_set_timing): CUDA events on the launch stream around each hot kernel
   int timing = 0;
@@ -358,7 +361,7 @@ int bm_destroy(bm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -995,6 +998,64 @@ int bm_sample(bm_ctx* c, int n, int rule, int start_site, const double* U_host, 
   c->launches++;
   KCHECK();
   CU(cudaMemcpyAsync(out_host, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BM_OK;
+}
+
+// a11, general masks (TNutils.py:2053-2116): unknown pixels (255) anywhere in ONE image.
+int bm_reconstruct_one(bm_ctx* c, const uint8_t* pixels_host, const double* u_host, int n_unknown, uint8_t* out_host) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(c->d == 2, "bm_reconstruct_one: binary pixels only");
+  REQUIRE(pixels_host && out_host && (n_unknown == 0 || u_host), "bm_reconstruct_one: bad arguments");
+  for (int j = 0; j < c->L; ++j) REQUIRE(c->sDl[j] > 0 && (j == c->L - 1 || c->sDr[j] == c->sDl[j + 1]), "bm_reconstruct_one: MPS not fully set");
+  CU(cudaSetDevice(c->device));
+  const int L = c->L, D = c->Dcap;
+  const size_t esz = (size_t)D * D;
+  if (!c->recE) {
+    DALLOC(c->recE, esz * (L + 1)); DALLOC(c->recT, esz); DALLOC(c->recV[0], D); DALLOC(c->recV[1], D);
+    DALLOC(c->recU, L); DALLOC(c->recPix, L); DALLOC(c->recCount, 1);
+  }
+  int cnt = 0;
+  for (int j = 0; j < L; ++j) { REQUIRE(pixels_host[j] <= 1 || pixels_host[j] == 255, "bm_reconstruct_one: pixels must be 0, 1 or 255"); cnt += pixels_host[j] == 255; }
+  REQUIRE(cnt == n_unknown, "bm_reconstruct_one: number of uniforms must equal the number of unknown pixels");
+  CU(cudaMemcpyAsync(c->recPix, pixels_host, L, cudaMemcpyHostToDevice, c->stream));
+  if (n_unknown) CU(cudaMemcpyAsync(c->recU, u_host, (size_t)n_unknown * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->recCount, 0, sizeof(int), c->stream));
+  const double one = 1.0, zero = 0.0;
+  // ---- right pass: E_L = [1]; E_j = sum_x M_j[x] E_{j+1} M_j[x]^T  (row-major; cuBLAS sees the transposes)
+  CU(cudaMemcpyAsync(c->recE + esz * L, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  for (int j = L - 1; j >= 1; --j) {
+    const int Dl = c->sDl[j], Dr = c->sDr[j], ldr = even(Dr);
+    double* Ej = c->recE + esz * j;
+    const double* En = c->recE + esz * (j + 1);
+    bool first = true;
+    for (int x = 0; x < 2; ++x) {
+      const int pixel = 1 - x;                                   // physical index x <-> pixel 1-x
+      if (pixels_host[j] != 255 && pixels_host[j] != pixel) continue;
+      const double* M = c->Lf(j) + (size_t)x * ldr;              // row-major (Dl x Dr), ld = 2*ldr
+      // T = M E_{j+1}  (Dl x Dr): column-major view T^T (Dr x Dl) = E^T M^T = E M^T (E symmetric)
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, Dr, Dl, Dr, &one, En, D, M, 2 * ldr, &zero, c->recT, D));
+      // E_j (+)= T M^T (Dl x Dl): column-major view E_j^T = M T^T -> gemm(op_T on M view, N on T view)
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, Dl, Dl, Dr, &one, M, 2 * ldr, c->recT, D, first ? &zero : &one, Ej, D));
+      first = false;
+    }
+    k_rescale_matrix<<<1, 256, 0, c->stream>>>(Ej, Dl, D, nullptr);
+    c->launches++;
+  }
+  KCHECK();
+  // ---- left pass
+  int cur = 0;
+  CU(cudaMemcpyAsync(c->recV[0], &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  for (int j = 0; j < L; ++j) {
+    const int Dl = c->sDl[j], Dr = c->sDr[j], ldr = even(Dr);
+    size_t shm = (size_t)(2 * Dr + 16) * sizeof(double);
+    k_rec_site<<<1, 256, shm, c->stream>>>(c->Lf(j), Dl, Dr, ldr, c->recE + esz * (j + 1), D, c->recV[cur], c->recV[cur ^ 1],
+                                           c->recPix, j, c->recU, c->recCount);
+    c->launches++;
+    cur ^= 1;
+  }
+  KCHECK();
+  CU(cudaMemcpyAsync(out_host, c->recPix, L, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return BM_OK;
 }

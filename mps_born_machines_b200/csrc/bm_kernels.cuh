@@ -1220,6 +1220,74 @@ __global__ void k_finish_logpsi(const double* __restrict__ E, int ld, const int*
   sign[i] = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// General-mask reconstruction of ONE image (reconstruct, TNutils.py:2053-2116).
+//   Right pass (host loop, cuBLAS): E_j = sum_{x allowed at site j} M_j[x] E_{j+1} M_j[x]^T, E_L = [1]   (Dl_j x Dl_j)
+//   Left pass (this kernel, one CTA per site, launched in site order): v <- v M_j[x] for known pixels; for unknown ones
+//   q_x = (v M_j[x]) E_{j+1} (v M_j[x])^T, P(pixel 0) = q_{phys 1} / (q_0 + q_1), accept pixel 0 iff u < P (the single-image
+//   rule of generate_sample, :1950/:1972/:1990), continue with the chosen branch.  v is rescaled by a power of two.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rec_site(const double* __restrict__ Lf, int Dl, int Dr, int ldr,
+                                                  const double* __restrict__ Enext, int ldE,   // (Dr x Dr), row-major
+                                                  const double* __restrict__ vin, double* __restrict__ vout,
+                                                  uint8_t* __restrict__ pix, int site, const double* __restrict__ u, int* __restrict__ ucount) {
+  extern __shared__ double shm[];          // w0[Dr], w1[Dr], red[...]
+  double* w0 = shm; double* w1 = shm + Dr; double* red = shm + 2 * Dr;
+  __shared__ int choice;
+  const int tid = threadIdx.x;
+  const int known = pix[site];             // pixel value 0/1, 255 = unknown
+  // w_x[b] = sum_a v[a] * M[a][x][b]   (L-form: Lf[(a*2 + x)*ldr + b])
+  for (int b = tid; b < Dr; b += 256) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int a = 0; a < Dl; ++a) {
+      double va = vin[a];
+      s0 = fma(va, Lf[((long long)a * 2 + 0) * ldr + b], s0);
+      s1 = fma(va, Lf[((long long)a * 2 + 1) * ldr + b], s1);
+    }
+    w0[b] = s0; w1[b] = s1;
+  }
+  __syncthreads();
+  if (known == 255) {
+    // q_x = w_x^T E w_x
+    double q0 = 0.0, q1 = 0.0;
+    for (int r = tid; r < Dr; r += 256) {
+      double t0 = 0.0, t1 = 0.0;
+      const double* er = Enext + (long long)r * ldE;
+      for (int c = 0; c < Dr; ++c) { double e = er[c]; t0 = fma(e, w0[c], t0); t1 = fma(e, w1[c], t1); }
+      q0 = fma(w0[r], t0, q0); q1 = fma(w1[r], t1, q1);
+    }
+    double a0 = block_sum(q0, red), a1 = block_sum(q1, red);
+    if (tid == 0) {
+      int k = atomicAdd(ucount, 1);
+      double p_pixel0 = a1 / (a0 + a1);              // pixel 0 <-> physical index 1
+      int pixel = (u[k] < p_pixel0) ? 0 : 1;
+      pix[site] = (uint8_t)pixel;
+      choice = 1 - pixel;                            // physical index of the chosen branch
+    }
+  } else if (tid == 0) choice = 1 - known;
+  __syncthreads();
+  const double* w = choice == 0 ? w0 : w1;
+  double m = 0.0;
+  for (int b = tid; b < Dr; b += 256) m = fmax(m, fabs(w[b]));
+  double mx = block_max(m, red);
+  __shared__ double scale;
+  if (tid == 0) scale = pow2d(-frexp_exp(mx));
+  __syncthreads();
+  for (int b = tid; b < Dr; b += 256) vout[b] = w[b] * scale;
+}
+
+// E (n x n, row-major ld) /= 2^e with e = exponent of max|E|  (keeps the right-environment chain in range)
+__global__ void __launch_bounds__(256) k_rescale_matrix(double* __restrict__ E, int n, int ld, double* __restrict__ scratch) {
+  __shared__ double red[8];
+  __shared__ double sc;
+  double m = 0.0;
+  for (long long i = threadIdx.x; i < (long long)n * n; i += 256) m = fmax(m, fabs(E[(i / n) * ld + (i % n)]));
+  double mx = block_max(m, red);
+  if (threadIdx.x == 0) sc = pow2d(-frexp_exp(mx));
+  __syncthreads();
+  for (long long i = threadIdx.x; i < (long long)n * n; i += 256) E[(i / n) * ld + (i % n)] *= sc;
+}
+
 // counter-based uniforms in [0,1): splitmix64(seed, site, sample) >> 11 * 2^-53
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;

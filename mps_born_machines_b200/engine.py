@@ -284,6 +284,16 @@ class BornEngine:
         check(self._ctx, self._lib.bm_sample(self._ctx, n, RULE[rule], start_site, up, C.c_uint64(seed), pp, _ptr(out)))
         return out
 
+    def reconstruct_one(self, img, u):
+        """reconstruct (TNutils.py:2053-2116) for one image with -1 (unknown) pixels anywhere; `u`: one uniform per
+        unknown pixel in site order.  Returns the completed image."""
+        a = np.asarray(img)
+        px = np.ascontiguousarray(np.where(a < 0, 255, a).astype(np.uint8))
+        uu = np.ascontiguousarray(np.asarray(u, dtype=np.float64))
+        out = np.empty(self.L, dtype=np.uint8)
+        check(self._ctx, self._lib.bm_reconstruct_one(self._ctx, _ptr(px), _ptr(uu) if uu.size else None, int(uu.size), _ptr(out)))
+        return out
+
     def sample_device_ms(self, n, seed=0, rule='batched'):
         ms = C.c_float()
         check(self._ctx, self._lib.bm_sample_device(self._ctx, n, RULE[rule], C.c_uint64(seed), C.byref(ms)))

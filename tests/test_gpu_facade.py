@@ -124,5 +124,14 @@ def test_generate_sample_and_reconstruct(T):
     np.random.seed(12)
     u = [np.random.rand() for _ in range(8)]
     assert np.array_equal(rec, o.reconstruct(arrays, corr, u))
-    with pytest.raises(NotImplementedError):
-        T.reconstruct(mps, T.partial_removal_img(img, (4, 4), .5, 0, 1))
+    # general masks (known suffix, columns removed, scattered): same bits as the reference procedure
+    rng = np.random.default_rng(5)
+    masks = [T.partial_removal_img(img, (4, 4), .5, 0, 1), T.partial_removal_img(img, (4, 4), .5, 1, 0),
+             T.partial_removal_img(img, (4, 4), .5, 1, 1), np.where(rng.random(16) < 0.5, -1, img), np.full(16, -1)]
+    for i, corr in enumerate(masks):
+        for rep in range(6):
+            np.random.seed(100 + 10 * i + rep)
+            rec = T.reconstruct(mps, corr)
+            np.random.seed(100 + 10 * i + rep)
+            u = [np.random.rand() for _ in range(int((corr == -1).sum()))]
+            assert np.array_equal(rec, o.reconstruct(arrays, corr, u)), (i, rep)

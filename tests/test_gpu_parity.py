@@ -371,3 +371,21 @@ def test_tf32_training_nll_within_1e3(bm):
         cost.append(eng.nll(imgs, 0))
     np.testing.assert_allclose(cost, cost_o, rtol=1e-3)
     eng.close()
+
+
+def test_general_mask_reconstruction_long_chain(bm):
+    """reconstruct with unknown pixels anywhere (TNutils.py:2053-2116) on a 28x28 chain: top half / left half /
+    right half removed and scattered pixels, bit-exact with the oracle's reduced-chain + right-canonise procedure."""
+    L, D = 784, 8
+    mps, imgs = make_problem(L, D, 3, 171, p_on=0.2)
+    eng = engine_for(bm, mps)
+    rng = np.random.default_rng(172)
+    img = imgs[0]
+    masks = [o.partial_removal_img(img, (28, 28), .5, 0, 1), o.partial_removal_img(img, (28, 28), .5, 1, 0),
+             o.partial_removal_img(img, (28, 28), .5, 1, 1), np.where(rng.random(L) < 0.3, -1, img)]
+    for corr in masks:
+        u = rng.random(int((corr == -1).sum()))
+        got = eng.reconstruct_one(corr, u)
+        want = o.reconstruct(mps, corr, u)
+        assert np.array_equal(got, want)
+    eng.close()
