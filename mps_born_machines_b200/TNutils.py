@@ -16,6 +16,7 @@ canonicalisation) and for the tiny object plumbing the reference API imposes.
 """
 import copy as _copy
 import math
+import os
 
 import numpy as np
 
@@ -25,7 +26,8 @@ from .engine import BornEngine, sweep_schedule
 __all__ = ['Tensor', 'MPS', 'initialize_mps', 'stater', 'tens_picture', 'left_right_cache', 'sequential_update',
            'computepsi', 'computeNLL', 'computeNLL_cached', 'learning_step_cached', 'learning_epoch_cached',
            'compress', 'compress_copy', 'compress2', 'generate_samples', 'generate_sample', 'reconstruct',
-           'bars_n_stripes', 'partial_removal_img', 'mps_lr', 'lr_update', 'zero', 'one', 'ImgCache']
+           'bars_n_stripes', 'partial_removal_img', 'mps_lr', 'lr_update', 'zero', 'one', 'ImgCache',
+           'training_and_probing', 'mps_checkpoint', 'generate_and_save', 'save_mps_sets', 'load_mps_sets', 'meanpool2d']
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -634,3 +636,96 @@ def reconstruct(mps, corr_img):
     res = corr_img.copy()
     res[start:] = out[0, start:]
     return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# experiment harness, checkpoints (TNutils.py:1682-1733, :2265-2291, :2317-2377) — host-side conveniences.
+# quimb pickles are replaced by an open .npz format (site tensors in the reference layout).
+# ---------------------------------------------------------------------------------------------------
+def _save_mps(mps, path):
+    np.savez(path, n_sites=len(mps.tensors), **{f'site{k}': t.data for k, t in enumerate(mps.tensors)})
+
+
+def _load_mps(path):
+    f = np.load(path)
+    return MPS([f[f'site{k}'] for k in range(int(f['n_sites']))])
+
+
+def save_mps_sets(mps, train_set, foldname, test_set=[]):
+    """TNutils.py:2265-2278 (mps stored as ./foldname/mps.npz instead of a quimb pickle)."""
+    if not os.path.exists('./' + foldname):
+        os.makedirs('./' + foldname)
+    _save_mps(mps, './' + foldname + '/mps.npz')
+    np.save('./' + foldname + '/train_set.npy', train_set)
+    if len(test_set) > 0:
+        np.save('./' + foldname + '/test_set.npy', test_set)
+
+
+def load_mps_sets(foldname):
+    """TNutils.py:2280-2291."""
+    mps = _load_mps('./' + foldname + '/mps.npz')
+    train_set = np.load('./' + foldname + '/train_set.npy')
+    test_set = np.load('./' + foldname + '/test_set.npy') if os.path.isfile('./' + foldname + '/test_set.npy') else None
+    return mps, train_set, test_set
+
+
+def mps_checkpoint(mps, imgs, val_imgs, period, periods, train_cost, val_cost, path='./'):
+    """TNutils.py:2317-2342: folder T{N}_L{L}/, file {period}I{periods-1}.mps(.npz), previous period's file removed,
+    trainloss.npy / valloss.npy, and at period 0 the data sets.  No optimiser / RNG state is saved (as in the
+    reference): resuming = load the tensors and rebuild the caches with left_right_cache."""
+    oldfilename = str(period - 1) + 'I' + str(periods - 1)
+    filename = str(period) + 'I' + str(periods - 1)
+    foldname = 'T' + str(len(imgs)) + '_L' + str(len(mps.tensors))
+    if not os.path.exists(path + foldname):
+        os.makedirs(path + foldname)
+    if os.path.isfile(path + foldname + '/' + oldfilename + '.mps.npz'):
+        os.remove(path + foldname + '/' + oldfilename + '.mps.npz')
+    _save_mps(mps, path + foldname + '/' + filename + '.mps.npz')
+    np.save(path + foldname + '/trainloss', train_cost)
+    np.save(path + foldname + '/valloss', val_cost)
+    if period == 0:
+        np.save(path + foldname + '/train_set.npy', imgs)
+        np.save(path + foldname + '/val_set.npy', val_imgs)
+    return path + foldname + '/'
+
+
+def generate_and_save(mps, period_samples, period, periods, period_epochs, imgs, shape, path='./'):
+    """TNutils.py:2344-2377 without the matplotlib figure (SVG output is skipped when matplotlib is unavailable);
+    the generated images are saved as gen_imgs/{period}.npy like the reference."""
+    gen_imgs = generate_samples(mps, period_samples) if period_samples > 1 else generate_sample(mps)
+    if not os.path.exists(path + '/gen_imgs'):
+        os.mkdir(path + '/gen_imgs')
+    np.save(path + '/gen_imgs/' + str(period) + '.npy', gen_imgs)
+    return gen_imgs
+
+
+def training_and_probing(period_epochs, periods, mps, shape, imgs, _imgs, img_cache, batch_size, lr, lr_update,
+                         update_wrap, val_imgs=[], period_samples=0, corrupted_set=None, plot=False, **kwargs):
+    """TNutils.py:1682-1733: periods x period_epochs of learning_epoch_cached with NLL probing, checkpoints and
+    sample generation after every period.  Returns (train_costs, samples)."""
+    train_costs = [computeNLL(mps, imgs, 0)]
+    val_costs = []
+    if len(val_imgs) > 0:
+        val_costs.append(computeNLL(mps, val_imgs, 0))
+    samples = []
+    for period in range(periods):
+        costs, lr = learning_epoch_cached(mps, imgs, _imgs, period_epochs, lr, img_cache, lr_update=lr_update,
+                                          update_wrap=update_wrap, batch_size=batch_size, **kwargs)
+        train_costs.extend(costs)
+        if len(val_imgs) > 0:
+            val_costs.append(computeNLL(mps, val_imgs, 0))
+        where = mps_checkpoint(mps, imgs, val_imgs, period, periods, train_costs, val_costs)
+        if period_samples > 0:
+            samples.append(generate_and_save(mps, period_samples, period, periods, period_epochs, imgs, shape, path=where))
+    return train_costs, samples
+
+
+def meanpool2d(npmnist, shape, grayscale_threshold=0.3):
+    """TNutils.py:2293-2315: 2x2 mean pooling of flattened images followed by re-binarisation."""
+    npmnist = np.asarray(npmnist, dtype=np.float64)
+    ds = []
+    for img in npmnist:
+        a = img.reshape(shape)
+        pooled = a.reshape(shape[0] // 2, 2, shape[1] // 2, 2).mean(axis=(1, 3))
+        ds.append((pooled.reshape(-1) > grayscale_threshold).astype(np.float64))
+    return np.array(ds)

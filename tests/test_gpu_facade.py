@@ -1,4 +1,6 @@
 """GPU tests of the TNutils-compatible facade: the reference notebooks' call sequences run unchanged."""
+import os
+
 import numpy as np
 import pytest
 
@@ -135,3 +137,22 @@ def test_generate_sample_and_reconstruct(T):
             np.random.seed(100 + 10 * i + rep)
             u = [np.random.rand() for _ in range(int((corr == -1).sum()))]
             assert np.array_equal(rec, o.reconstruct(arrays, corr, u)), (i, rep)
+
+
+def test_training_and_probing(T, tmp_path, monkeypatch):
+    """tests/grownup_tests.ipynb flow: periods x epochs with probing, checkpoints and sample generation."""
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(8)
+    imgs = o.bars_n_stripes_all(4)
+    mps = T.initialize_mps(16, 2)
+    data = np.array([T.tens_picture(img) for img in imgs])
+    cache = T.left_right_cache(mps, data)
+    costs, samples = T.training_and_probing(2, 2, mps, (4, 4), imgs, data, cache, 30, 0.3, lambda x: x * 0.95,
+                                            lambda site, div: div, val_imgs=imgs[:5], period_samples=4, max_bond=8)
+    assert len(costs) == 1 + 2 * 2 and costs[-1] < costs[0]
+    assert len(samples) == 2 and samples[0].shape == (4, 16)
+    mps2, tr, _ = None, None, None
+    where = f'T30_L16/'
+    assert os.path.isfile(where + '1I1.mps.npz') and os.path.isfile(where + 'gen_imgs/1.npy')
+    loaded = T._load_mps(where + '1I1.mps.npz')
+    assert abs(T.computeNLL(loaded, imgs, 0) - costs[-1]) < 1e-9          # resume = reload tensors (same NLL)

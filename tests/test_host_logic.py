@@ -156,3 +156,28 @@ def test_two_rank_gloo_gradient_allreduce_equals_single_process():
         assert abs(buf[-2] - lnsum) < 1e-9 * abs(lnsum) and buf[-1] == 0
         assert drift == 0.0
     assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])   # bitwise identical replicas
+
+
+def test_facade_save_load_and_meanpool(tmp_path, monkeypatch):
+    """tests/test_functions.ipynb:598,750: the state is invariant under save/load; meanpool2d vs the reference loop."""
+    from mps_born_machines_b200 import TNutils as T
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(1)
+    mps = T.initialize_mps(8, 3)
+    train = (np.random.random((5, 8)) < 0.5).astype(int)
+    T.save_mps_sets(mps, train, 'run1', test_set=train[:2])
+    m2, tr, te = T.load_mps_sets('run1')
+    assert all(np.array_equal(a.data, b.data) for a, b in zip(mps.tensors, m2.tensors))
+    assert np.array_equal(tr, train) and np.array_equal(te, train[:2])
+    where = T.mps_checkpoint(mps, train, train[:2], 0, 3, [1.0], [2.0], path=str(tmp_path) + '/')
+    assert os.path.isfile(where + '0I2.mps.npz') and os.path.isfile(where + 'train_set.npy')
+    T.mps_checkpoint(mps, train, train[:2], 1, 3, [1.0, 0.9], [2.0, 1.9], path=str(tmp_path) + '/')
+    assert not os.path.isfile(where + '0I2.mps.npz') and os.path.isfile(where + '1I2.mps.npz')
+    assert np.array_equal(np.load(where + 'trainloss.npy'), [1.0, 0.9])
+    imgs = np.random.random((3, 16))
+    want = []
+    for img in imgs:                       # TNutils.py:2299-2314
+        a = img.reshape(4, 4)
+        want.append([np.mean([a[c, r], a[c, r + 1], a[c + 1, r], a[c + 1, r + 1]]) for c in range(0, 4, 2) for r in range(0, 4, 2)])
+    want = (np.array(want) > 0.3).astype(float)
+    assert np.array_equal(T.meanpool2d(imgs, (4, 4)), want)
