@@ -389,3 +389,67 @@ def test_general_mask_reconstruction_long_chain(bm):
         want = o.reconstruct(mps, corr, u)
         assert np.array_equal(got, want)
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# shapes that take the unpredicated interior fast path (bond multiple of 16, full 64-row tiles) and edge groupings
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('D,N,precision', [(32, 2500, 'fp64'), (48, 1100, 'fp64'), (64, 3000, 'tf32')])
+def test_full_tile_fast_path_parity(bm, D, N, precision):
+    L = 14
+    mps, imgs = make_problem(L, D, N, 201 + D, p_on=0.35, centre=6)
+    phys = o.embed(imgs)
+    eng = bm.BornEngine(L, D, precision=precision)
+    eng.set_mps(mps); eng.set_data(imgs)
+    cache = o.EnvCache(mps, phys, 'maxabs')
+    eng.env_build(6)
+    for j in (3, 6):
+        np.testing.assert_allclose(eng.env_get(0, j), normed(cache.lenv[j]), rtol=TIGHT, atol=1e-13)
+    for j in (8, 11):
+        np.testing.assert_allclose(eng.env_get(1, j), normed(cache.renv[j]), rtol=TIGHT, atol=1e-13)
+    _, lp = o.logpsi(mps, phys)
+    mps_o = [t.copy() for t in mps]
+    cpow = o.EnvCache(mps_o, phys, 'pow2')
+    tol = RTOL if precision == 'fp64' else 2e-3
+    for k in (6, 7):
+        ref = o.two_site_step(mps_o, k, cpow.lenv[k], cpow.renv[k + 2], phys[:, k], phys[:, k + 1], 0.01, True, 'l2', max_bond=D)
+        S = eng.step_grad(k)
+        if k == 6:
+            np.testing.assert_allclose(eng.last_logpsi(), lp, rtol=1e-9)
+            Sg = eng.grad_to_ref(k, S)
+            assert np.abs(Sg - ref['S']).max() < (1e-9 if precision == 'fp64' else 3e-3) * np.abs(ref['S']).max()
+        out = eng.step_update(k, S, N, 0.01, True, 'l2', D, 1e-10, 0.0, True)
+        assert out['chi'] == ref['s'].size
+        np.testing.assert_allclose(out['s'], ref['s'], rtol=tol)
+        eng.env_advance(k, True)
+        o.write_back(mps_o, k, ref['left'], ref['right']); cpow.advance_right(mps_o, k)
+        if precision == 'tf32':
+            break          # the trajectories separate at 1e-3 after a TF32 step: one teacher-forced step only
+    eng.close()
+
+
+def test_sampler_large_ragged_bond_bit_exact(bm):
+    """bond 300 (not a multiple of the 16-wide k-chunk, wider than two 128-column tiles), 900 samples."""
+    L, D, N = 24, 300, 900
+    mps, _ = make_problem(L, D, 1, 211)
+    U = np.random.default_rng(212).random((L, N))
+    eng = engine_for(bm, mps, cap=D)
+    got = eng.sample(N, U=U, rule='batched')
+    assert np.array_equal(got, o.generate_samples(mps, U, rescale=True).astype(np.uint8))
+    eng.close()
+
+
+def test_degenerate_groupings(bm):
+    """all images identical (three of the four pixel-pair groups are empty at every bond) and a single sample."""
+    L, D = 8, 6
+    mps, _ = make_problem(L, D, 1, 221, centre=3)
+    for imgs in (np.tile((np.arange(L) % 2)[None, :], (70, 1)), np.ones((1, L), dtype=np.int64)):
+        phys = o.embed(imgs)
+        eng = engine_for(bm, mps, imgs)
+        cache = o.EnvCache(mps, phys, 'pow2')
+        ref = o.two_site_step(mps, 3, cache.lenv[3], cache.renv[5], phys[:, 3], phys[:, 4], 0.05, True, 'l2', max_bond=12)
+        out = eng.step(3, 0.05, True, 'l2', max_bond=12, want_s=True, advance=False)
+        assert out['chi'] == ref['s'].size
+        np.testing.assert_allclose(out['s'], ref['s'], rtol=RTOL)
+        np.testing.assert_allclose(out['sum_logpsi'], np.log(np.abs(ref['psi'])).sum() + (cache.ls_l[3] + cache.ls_r[5]).sum(), rtol=1e-9)
+        eng.close()
