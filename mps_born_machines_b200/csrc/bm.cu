@@ -445,6 +445,8 @@ int bm_set_data(bm_ctx* c, const uint8_t* pixels_host, int n) {
     kchunk = std::max(KC, std::min(GRAD_MAXCHUNK, ((kchunk + KC - 1) / KC) * KC));
     c->last_kchunk = kchunk;
     c->ws_slots = (n + kchunk - 1) / kchunk;
+    // room for one split per SM even when a single pixel-pair group holds every sample (TF32 kernel: 1 tile per item)
+    if (n >= 16 * c->n_sm) c->ws_slots = std::max(c->ws_slots, c->n_sm + 8);
     DALLOC(c->ws, (size_t)c->ws_slots * c->d * c->Dcap * c->d * c->ldcap);
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -639,7 +641,9 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
         }
         if (ns > c->ws_slots) continue;
         double waves = std::ceil((double)items / c->n_sm);
-        double cost = waves * (kc + 24.0);            // + fixed per-item cost (prologue, partial-tile store)
+        // + fixed per-item cost in sample-equivalents (prologue, partial-tile store; the TF32 kernel stores a whole
+        //   Dl x Dr FP64 block per item, about the traffic of 130 samples)
+        double cost = waves * (kc + (tf32 ? 160.0 : 24.0));
         if (cost < best) { best = cost; kchunk = kc; nsplit = ns; }
       }
     }

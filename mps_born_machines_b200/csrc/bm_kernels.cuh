@@ -638,40 +638,46 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_grad_tf32(GradParams P, int* 
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(128, npad);
 
-  // staging: thread owns column (a or c) = tid, for every 4-sample chunk of the stage
+  // staging: thread `tid` owns column tid of L (a) and of R (c).  Work unit = 16 samples (half a stage); the global
+  // loads of the next unit are issued before the current one is converted and stored, and the first half of the
+  // NEXT stage is already in flight across the barrier + MMA-issue gap (up to 64 loads per thread outstanding).
   const int nblk = (cnt + TF_KS - 1) / TF_KS;
-  bool alive = true;
-  for (int blk = 0; blk < nblk && alive; ++blk) {
-    const int st = blk % TF_STAGES;
-    if (blk >= TF_STAGES) alive = mbar_wait_bounded(bar0 + 8 * st, ((blk / TF_STAGES) - 1) & 1, status);   // MMAs that read this stage are done
-    const int n0 = blk * TF_KS;
-    unsigned char* dL = sm.L[st] + (tid & 7) * 16 + (tid >> 3) * TF_SBO;
-    unsigned char* dR = sm.R[st] + (tid & 7) * 16 + (tid >> 3) * TF_SBO;
-    // 16 samples at a time: issue all 32 global loads first (64 KB in flight per SM), then convert and store
+  auto issue = [&](int unit, double (&lv)[16], double (&rv)[16]) {
+    const int nb = unit * 16;
 #pragma unroll
-    for (int half = 0; half < TF_KS / 16; ++half) {
-      double lv[16], rv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + half * 16 + j;
-        lv[j] = 0.0; rv[j] = 0.0;
-        if (n < cnt) {
-          const long long id = sm.idx[n];
-          if (tid < P.Dl) lv[j] = P.Lenv[id * P.ldL + tid];
-          if (tid < P.Dr) rv[j] = P.Renv[id * P.ldR + tid];
-        }
-      }
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int ch = half * 4 + c4;
-        const int nb = n0 + half * 16 + c4 * 4;
-        float r[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = (nb + j < cnt) ? (float)(rv[c4 * 4 + j] * sm.w[nb + j]) : 0.f;
-        *reinterpret_cast<float4*>(dL + ch * TF_LBO) = make_float4((float)lv[c4 * 4], (float)lv[c4 * 4 + 1], (float)lv[c4 * 4 + 2], (float)lv[c4 * 4 + 3]);
-        *reinterpret_cast<float4*>(dR + ch * TF_LBO) = make_float4(r[0], r[1], r[2], r[3]);
+    for (int j = 0; j < 16; ++j) {
+      const int n = nb + j;
+      lv[j] = 0.0; rv[j] = 0.0;
+      if (n < cnt) {
+        const long long id = sm.idx[n];
+        if (tid < P.Dl) lv[j] = P.Lenv[id * P.ldL + tid];
+        if (tid < P.Dr) rv[j] = P.Renv[id * P.ldR + tid];
       }
     }
+  };
+  auto store = [&](int unit, const double (&lv)[16], const double (&rv)[16]) {
+    const int st = (unit >> 1) % TF_STAGES, half = unit & 1, nb = unit * 16;
+    unsigned char* dL = sm.L[st] + (tid & 7) * 16 + (tid >> 3) * TF_SBO + half * 4 * TF_LBO;
+    unsigned char* dR = sm.R[st] + (tid & 7) * 16 + (tid >> 3) * TF_SBO + half * 4 * TF_LBO;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = (nb + c4 * 4 + j < cnt) ? (float)(rv[c4 * 4 + j] * sm.w[nb + c4 * 4 + j]) : 0.f;
+      *reinterpret_cast<float4*>(dL + c4 * TF_LBO) = make_float4((float)lv[c4 * 4], (float)lv[c4 * 4 + 1], (float)lv[c4 * 4 + 2], (float)lv[c4 * 4 + 3]);
+      *reinterpret_cast<float4*>(dR + c4 * TF_LBO) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  };
+  bool alive = true;
+  double lvA[16], rvA[16], lvB[16], rvB[16];
+  issue(0, lvA, rvA);
+  for (int blk = 0; blk < nblk && alive; ++blk) {
+    const int st = blk % TF_STAGES;
+    issue(2 * blk + 1, lvB, rvB);
+    if (blk >= TF_STAGES) alive = mbar_wait_bounded(bar0 + 8 * st, ((blk / TF_STAGES) - 1) & 1, status);   // MMAs that read this stage are done
+    store(2 * blk, lvA, rvA);
+    if (blk + 1 < nblk) issue(2 * blk + 2, lvA, rvA);
+    store(2 * blk + 1, lvB, rvB);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> async proxy (UMMA reads)
     __syncthreads();
     if (tid == 0) {
@@ -701,16 +707,22 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_grad_tf32(GradParams P, int* 
     const int mt = warp >> 2;                       // warps 0-3: rows 0..127, warps 4-7: rows 128..255
     const int a = mt * 128 + (warp & 3) * 32 + lane;
     if (mt < mtiles) {
-      for (int c0 = 0; c0 < npad; c0 += 8) {
-        uint32_t r[8];
+      // 16 columns per tcgen05.ld: every thread then writes 128 contiguous bytes (full sectors) of its row
+      for (int c0 = 0; c0 < npad; c0 += 16) {
+        uint32_t r[16];
         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 256 + c0);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (a < P.Dl) {
+          double* orow = out + (long long)a * P.ldA + c0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (c0 + j < P.Dr) out[(long long)a * P.ldA + c0 + j] = (double)__uint_as_float(r[j]);
+          for (int j = 0; j < 16; j += 2) {
+            if (c0 + j + 1 < P.Dr)
+              *reinterpret_cast<double2*>(orow + j) = make_double2((double)__uint_as_float(r[j]), (double)__uint_as_float(r[j + 1]));
+            else if (c0 + j < P.Dr) orow[j] = (double)__uint_as_float(r[j]);
+          }
         }
       }
     }
