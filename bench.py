@@ -32,9 +32,11 @@ WORKLOADS = {
     # name: (N_total, L, D, first bond)
     'c3': (60000, 784, 256, 384),
     'c2': (1000, 784, 100, 384),
-    'c5': (10000, 784, 128, 384),
+    'c5': (10000, 784, 128, 384),        # BASELINE config 5 as worded: 4-level pixels as one-hot d=4 sites
+    'c5b': (10000, 1568, 128, 768),      # the reference's grayscale notebook: 2 bits per pixel, d stays 2, L doubles
     'tiny': (512, 64, 32, 24),
 }
+PHYS_DIM = {'c5': 4}
 FP64_PEAK_TFLOPS = 35.7   # measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_probe_fp64_svd.jsonl)
 
 
@@ -100,17 +102,19 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # the reference arm / CPU baseline: numpy float64 oracle port on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(N, D, steps, seed=5):
+def cpu_reference_steps(N, D, steps, seed=5, d=2):
     """Time `steps` two-site steps (TNutils.py:1510-1568 arithmetic + sequential_update) of the oracle port
     at bond dimension D on N samples with all host BLAS threads.  Environments are synthetic random vectors
     (the arithmetic and its cost do not depend on their values); pixel statistics are those of the workload."""
     from oracle import born_oracle as o
     rng = np.random.default_rng(seed)
     imgs = o.synthetic_images(N, 4)           # 4 sites are enough: columns 1,2 play bonds k,k+1
-    phys = o.embed(imgs)
+    if d > 2:
+        imgs = rng.integers(0, d, size=imgs.shape)
+    phys = o.embed(imgs, d)
     # 4-site MPS with open bonds D in the middle: sites 1,2 are the pair being optimised
-    mps3 = [rng.standard_normal((1, D, 2)) / math.sqrt(2 * D), rng.standard_normal((D, D, 2)) / math.sqrt(2 * D),
-            rng.standard_normal((D, D, 2)) / math.sqrt(2 * D), rng.standard_normal((D, 1, 2)) / math.sqrt(2 * D)]
+    mps3 = [rng.standard_normal((1, D, d)) / math.sqrt(d * D), rng.standard_normal((D, D, d)) / math.sqrt(d * D),
+            rng.standard_normal((D, D, d)) / math.sqrt(d * D), rng.standard_normal((D, 1, d)) / math.sqrt(d * D)]
     mps = o.from_site3(mps3)
     lv = rng.standard_normal((N, D)); rv = rng.standard_normal((N, D))
     times = []
@@ -131,11 +135,12 @@ def run_reference(args):
         return
     N, L, D, k0 = WORKLOADS[args.workload]
     cores = os.cpu_count()
-    cpu_reference_steps(min(N, 2000), D, 1)                       # warm BLAS
+    dd = PHYS_DIM.get(args.workload, 2)
+    cpu_reference_steps(min(N, 2000), D, 1, d=dd)                 # warm BLAS
     t = []
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_steps(N, D, 1)
-    t = cpu_reference_steps(N, D, args.steps)
+        cpu_reference_steps(N, D, 1, d=dd)
+    t = cpu_reference_steps(N, D, args.steps, d=dd)
     ms = 1e3 * float(np.mean(t))
     value = N / float(np.mean(t))
     line = {
@@ -182,12 +187,16 @@ def run_ours(args):
 
     # ---- set-up (untimed): data shard, MPS with the centre at the first bond, environments
     t_setup = time.time()
-    imgs = mpslib.synthetic_images(N, L)
+    d = PHYS_DIM.get(args.workload, 2)
+    if d == 2:
+        imgs = mpslib.synthetic_images(N, L)
+    else:   # 4-level synthetic images: two independent bit planes of the prototype mixture
+        imgs = 2 * mpslib.synthetic_images(N, L, seed=1234) + mpslib.synthetic_images(N, L, seed=4321, p_on=0.3)
     per = (N + world - 1) // world
     shard = imgs[rank * per:min(N, (rank + 1) * per)]
     start = k0 - warm
-    mps = mpslib.random_mps(L, D, rng=np.random.default_rng(11), centre=start)
-    eng = BornEngine(L, D, device=local, svd=args.svd, precision=args.precision)
+    mps = mpslib.random_mps(L, D, d=d, rng=np.random.default_rng(11), centre=start)
+    eng = BornEngine(L, D, phys_dim=d, device=local, svd=args.svd, precision=args.precision)
     eng.set_data(shard, n_total=N)
     eng.set_mps(mps)
     eng.env_build(start)
@@ -267,7 +276,7 @@ def run_ours(args):
     eng.set_timing(False)
     n_loc = shard.shape[0]
     ker = {}
-    for name, flops in (('grad', 2.0 * D * D * n_loc), ('psi', 2.0 * D * D * n_loc), ('env_advance', 2.0 * D * D * n_loc)):
+    for name, flops in (('grad', 2.0 * D * D * n_loc), ('psi', 2.0 * D * D * n_loc), ('env_advance', 2.0 * D * D * n_loc)):   # independent of d
         ms, cnt = tim[name]
         if cnt:
             ker[name] = {'ms': ms / cnt, 'tflops': flops / (ms / cnt * 1e-3) / 1e12}
@@ -288,7 +297,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             cs = max(2, min(8, int(20.0 / max(0.05, 1.5e-5 * N * D / 256))))
-            tcpu = cpu_reference_steps(N, D, cs)
+            tcpu = cpu_reference_steps(N, D, cs, d=d)
             cpu = {'value': N / float(np.mean(tcpu)), 'unit': 'sample·site updates/s', 'cores': os.cpu_count(), 'kind': 'port',
                    'sample': f'{cs} mid-chain two-site steps at N={N}, D={D} (numpy float64 oracle port, all host cores)'}
         line = {
