@@ -63,7 +63,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.gpu), '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          '-i', str(self.gpu), '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -286,8 +286,11 @@ def run_ours(args):
             ker[name] = {'ms': ms / cnt}
     dom = max(('grad', 'psi', 'env_advance'), key=lambda n: ker.get(n, {'ms': 0})['ms'])
     peaks, peak_src = load_peaks()
+    # dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/r01_ncu_summary.md);
+    # only valid for the configuration that was captured (c3, one GPU, FP64)
+    traffic = 255.7e6 if (args.workload == 'c3' and world == 1 and not args.samples and dom == 'psi') else None
     roofline = {'bound': 'tensor', 'kernel': 'k_' + dom, 'achieved': ker[dom]['tflops'], 'peak': FP64_PEAK_TFLOPS,
-                'unit': 'TFLOP/s', 'frac': ker[dom]['tflops'] / FP64_PEAK_TFLOPS, 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': ker[dom]['tflops'] / FP64_PEAK_TFLOPS, 'traffic': traffic,
                 'peak_source': 'FP64: cuBLAS DGEMM 8192^3 sustained measured by tools/probe on this pool (FP64 is not in '
                                'MEASURED_PEAKS.json; tcgen05 has no FP64 kind, DMMA.8x8x4 issue peak measured 37.1); '
                                f'MEASURED_PEAKS.json {peak_src}',
