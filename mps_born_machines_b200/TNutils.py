@@ -27,6 +27,8 @@ __all__ = ['Tensor', 'MPS', 'initialize_mps', 'stater', 'tens_picture', 'left_ri
            'computepsi', 'computeNLL', 'computeNLL_cached', 'learning_step_cached', 'learning_epoch_cached',
            'compress', 'compress_copy', 'compress2', 'generate_samples', 'generate_sample', 'reconstruct',
            'bars_n_stripes', 'partial_removal_img', 'mps_lr', 'lr_update', 'zero', 'one', 'ImgCache',
+           'torchized_mps', 'torchized_imgs', 'torchized_cache', 'sequential_update_torched', 'learning_epoch_torched',
+           'computeNLL_torched', 'training_and_probing_torched', 'cached_stochastic_learning_epoch',
            'training_and_probing', 'mps_checkpoint', 'generate_and_save', 'save_mps_sets', 'load_mps_sets', 'meanpool2d']
 
 
@@ -729,3 +731,92 @@ def meanpool2d(npmnist, shape, grayscale_threshold=0.3):
         pooled = a.reshape(shape[0] // 2, 2, shape[1] // 2, 2).mean(axis=(1, 3))
         ds.append((pooled.reshape(-1) > grayscale_threshold).astype(np.float64))
     return np.array(ds)
+
+
+# ---------------------------------------------------------------------------------------------------
+# G3 "torched" twins (TNutils.py:995-1378, :1735-1803) and the stochastic-cache epoch (:1633-1675), as shims.
+# In the reference these keep float32 torch copies of the sites / images / caches next to the quimb MPS and do the
+# contractions with torch.einsum; here the device state lives in the engine (FP64), so the handles are opaque.
+# The G3 step renormalises with A/sqrt(A.A) (:1257), so these drivers run the engine with renorm='l2'.
+# ---------------------------------------------------------------------------------------------------
+class _TorchHandle:
+    """what torchized_mps / torchized_imgs return: an opaque handle (indexable per site for len()/debugging)."""
+    def __init__(self, kind, payload):
+        self.kind, self.payload = kind, payload
+
+    def __len__(self):
+        return len(self.payload) if self.kind == 'mps' else self.payload.shape[1]
+
+
+def torchized_mps(mps, inds_dict):
+    """TNutils.py:995-1009: registers the site index names in inds_dict['mps'] like the reference."""
+    inds_dict.setdefault('mps', {})
+    for site, t in enumerate(mps.tensors):
+        inds_dict['mps'][site] = t.inds
+    return _TorchHandle('mps', mps)
+
+
+def torchized_imgs(_imgs, inds_dict):
+    """TNutils.py:1011-1027."""
+    pixels = _to_pixels(_imgs)
+    inds_dict.setdefault('imgs', {})
+    for site in range(pixels.shape[1]):
+        inds_dict['imgs'][site] = (f'v{site}',)
+    return _TorchHandle('imgs', pixels)
+
+
+def torchized_cache(torch_mps, torch_imgs, inds_dict, computing_psi=False):
+    """TNutils.py:1113-1149: left/right environments of all images -> device-resident ImgCache.
+    With computing_psi=True the reference returns (psi, cache) from the un-rescaled right chain (:1141-1148)."""
+    inds_dict.setdefault('cache', {})
+    mps, pixels = torch_mps.payload, torch_imgs.payload
+    cache = left_right_cache(mps, pixels)
+    if computing_psi:
+        sg, ln = cache.engine.logpsi(pixels)
+        return sg * np.exp(ln), cache
+    return cache
+
+
+def sequential_update_torched(torch_mps, torch_imgs, torch_cache, site, going_right, inds_dict, rescale=True):
+    """TNutils.py:1065-1111."""
+    return sequential_update(torch_mps.payload, torch_imgs.payload, torch_cache, site, going_right)
+
+
+def computeNLL_torched(mps, imgs, torch_mps, torch_imgs, inds_dict):
+    """TNutils.py:909-928: NLL of the training images assuming a right-canonical MPS (Z from site 0)."""
+    return computeNLL(mps, torch_imgs.payload, 0)
+
+
+def learning_epoch_torched(mps, imgs, torch_mps, torch_imgs, epochs, initial_lr, torch_cache, inds_dict,
+                           batch_size=25, update_wrap=None, lr_update=lambda lr: lr, **kwargs):
+    """TNutils.py:1288-1378 (L2 renormalisation, zero-psi steps skipped with the reference's message)."""
+    return learning_epoch_cached(mps, imgs, torch_imgs.payload, epochs, initial_lr, torch_cache, batch_size=batch_size,
+                                 update_wrap=update_wrap, lr_update=lr_update, renorm='l2', **kwargs)
+
+
+def training_and_probing_torched(period_epochs, periods, mps, inds_dict, torch_mps, shape, imgs, _imgs, torch_imgs,
+                                 torch_cache, batch_size, lr, update_wrap=None, lr_update=lambda lr: lr, val_imgs=[],
+                                 period_samples=0, corrupted_set=None, plot=False, path='./', **kwargs):
+    """TNutils.py:1735-1803."""
+    train_costs = [computeNLL(mps, imgs, 0)]
+    val_costs = [computeNLL(mps, val_imgs, 0)] if len(val_imgs) > 0 else []
+    samples = []
+    for period in range(periods):
+        costs, lr = learning_epoch_torched(mps, imgs, torch_mps, torch_imgs, period_epochs, lr, torch_cache, inds_dict,
+                                           batch_size=batch_size, update_wrap=update_wrap, lr_update=lr_update, **kwargs)
+        train_costs.extend(costs)
+        if len(val_imgs) > 0:
+            val_costs.append(computeNLL(mps, val_imgs, 0))
+        where = mps_checkpoint(mps, imgs, val_imgs, period, periods, train_costs, val_costs, path)
+        if period_samples > 0:
+            samples.append(generate_and_save(mps, period_samples, period, periods, period_epochs, imgs, shape, path=where))
+    return train_costs, samples
+
+
+def cached_stochastic_learning_epoch(mps, val_imgs, _imgs, epochs, lr, img_cache, last_dirs=None, last_sites=None,
+                                     last_epochs=None, batch_size=25, **kwargs):
+    """TNutils.py:1633-1675.  The reference refreshes per-image caches lazily (last_dirs/last_sites/last_epochs
+    bookkeeping, :586-625) to save CPU time; the device keeps every image's environments current, so the bookkeeping
+    arrays are accepted and ignored.  Returns the list of epoch NLLs like the reference."""
+    cost, _ = learning_epoch_cached(mps, val_imgs, _imgs, epochs, lr, img_cache, batch_size=batch_size, **kwargs)
+    return cost

@@ -196,6 +196,14 @@ class BornEngine:
             out['s'] = s[:out['chi']]
         return out
 
+    def canonize(self, centre):
+        """Move the orthogonality centre to `centre` on the device (quimb canonize, TNutils.py:398) by exact
+        (untruncated) splits: sites < centre become left isometries, sites > centre right isometries."""
+        for k in range(0, centre):
+            self.split_bond(k, going_right=True, max_bond=self.site_dims(k)[1], cutoff=0.0)
+        for k in range(self.L - 2, centre - 1, -1):
+            self.split_bond(k, going_right=False, max_bond=self.site_dims(k)[1], cutoff=0.0)
+
     def learning_step_host(self, k, site_k, site_k1, lr, going_right=True, **kw):
         """Reference-style call with HOST tensors in and out (learning_step_cached + write-back +
         sequential_update, TNutils.py:1603-1620): uploads the two site tensors, runs the step on the

@@ -156,3 +156,31 @@ def test_training_and_probing(T, tmp_path, monkeypatch):
     assert os.path.isfile(where + '1I1.mps.npz') and os.path.isfile(where + 'gen_imgs/1.npy')
     loaded = T._load_mps(where + '1I1.mps.npz')
     assert abs(T.computeNLL(loaded, imgs, 0) - costs[-1]) < 1e-9          # resume = reload tensors (same NLL)
+
+
+def test_torched_api_flow(T, tmp_path):
+    """notebooks/probing_ex.ipynb cells 7-11: the G3 (torch) call sequence, L2 renormalisation, minibatches."""
+    np.random.seed(9)
+    imgs = (np.random.random((40, 12)) < 0.4).astype(int)
+    _imgs = np.array([T.tens_picture(img) for img in imgs])
+    mps = T.initialize_mps(imgs.shape[1], bdim=4)
+    start = [t.copy() for t in mps.arrays()]
+    inds_dict = {'mps': {}, 'imgs': {}, 'cache': {}}
+    torch_mps = T.torchized_mps(mps, inds_dict)
+    torch_imgs = T.torchized_imgs(_imgs, inds_dict)
+    torch_cache = T.torchized_cache(torch_mps, torch_imgs, inds_dict)
+    assert inds_dict['mps'][1] == ('i0', 'i1', 'v1') and len(torch_imgs) == 12
+    costs, samples = T.training_and_probing_torched(2, 2, mps, inds_dict, torch_mps, (3, 4), imgs, _imgs, torch_imgs, torch_cache,
+                                                    40, 0.05, lr_update=lambda x: x * 0.95, period_samples=3,
+                                                    path=str(tmp_path) + '/', max_bond=8)
+    assert len(costs) == 5 and costs[-1] < costs[0] and len(samples) == 2
+    # full batch + l2 rule is gauge invariant: same curve as the plain oracle
+    cost_o, _ = o.learning_epoch_cached(start, imgs, 4, 0.05, renorm='l2', max_bond=8, lr_update=lambda x: x * 0.95)
+    np.testing.assert_allclose(costs[1:], cost_o, rtol=1e-6)
+    assert abs(T.computeNLL_torched(mps, imgs, torch_mps, torch_imgs, inds_dict) - costs[-1]) < 1e-9
+    psi, _ = T.torchized_cache(torch_mps, torch_imgs, inds_dict, computing_psi=True)
+    assert abs(-2 * np.log(np.abs(psi)).mean() + np.log(np.sum(mps[0].data ** 2)) - costs[-1]) < 1e-9
+    # stochastic epoch: minibatches of 10 through the same engine
+    np.random.seed(10)
+    c2 = T.cached_stochastic_learning_epoch(mps, imgs, _imgs, 1, 0.02, torch_cache, None, None, None, batch_size=10, max_bond=8)
+    assert len(c2) == 1 and np.isfinite(c2[0])

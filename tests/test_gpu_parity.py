@@ -453,3 +453,26 @@ def test_degenerate_groupings(bm):
         np.testing.assert_allclose(out['s'], ref['s'], rtol=RTOL)
         np.testing.assert_allclose(out['sum_logpsi'], np.log(np.abs(ref['psi'])).sum() + (cache.ls_l[3] + cache.ls_r[5]).sum(), rtol=1e-9)
         eng.close()
+
+
+def test_device_canonize(bm):
+    """canonicalisation on the device (exact splits): isometries on both sides of the centre, state unchanged."""
+    L, D = 10, 6
+    rng = np.random.default_rng(231)
+    raw = o.random_mps(L, D, rng=rng)                       # not canonical
+    imgs = (rng.random((25, L)) < 0.5).astype(np.int64)
+    eng = engine_for(bm, raw, cap=2 * D)
+    _, lp0 = eng.logpsi(imgs)
+    for centre in (0, 4, L - 1):
+        eng.canonize(centre)
+        can = eng.get_mps()
+        for k in range(centre):
+            m = o.site3(can, k)
+            np.testing.assert_allclose(np.einsum('abp,acp->bc', m, m), np.eye(m.shape[1]), atol=1e-11)
+        for k in range(centre + 1, L):
+            m = o.site3(can, k)
+            np.testing.assert_allclose(np.einsum('abp,cbp->ac', m, m), np.eye(m.shape[0]), atol=1e-11)
+        _, lp = eng.logpsi(imgs)
+        np.testing.assert_allclose(lp, lp0, rtol=1e-10)
+        assert abs(np.sum(can[centre] ** 2) - o.norm2_full(raw)) < 1e-10 * o.norm2_full(raw)
+    eng.close()
