@@ -451,10 +451,12 @@ def learning_step_cached(mps, index, _imgs, lr, img_cache, going_right=True,
     if isinstance(owner, mps_lr):
         if owner.t > 0:
             mom_bias = owner.momentum * owner.past_grad[index]
-    elif update_wrap is not None and not _is_identity(update_wrap):
-        raise NotImplementedError('arbitrary update_wrap callbacks are not supported by the device path; '
-                                  'use the identity or mps_lr.J')
-    out = eng.step(index, _lr_value(lr), going_right, renorm, max_bond, cutoff, mask, mom_bias, advance=False)
+    generic = update_wrap is not None and not isinstance(owner, mps_lr) and not _is_identity(update_wrap)
+    if generic:       # arbitrary callback: host round trip (download dNLL, call, upload the update)
+        out = eng.step_with_update_fn(index, _lr_value(lr), lambda site, dn: _as_array(update_wrap(site, _dnll_tensor(site, dn, len(mps.tensors)))).reshape(dn.shape),
+                                      going_right, renorm, max_bond, cutoff, mask, advance=False)
+    else:
+        out = eng.step(index, _lr_value(lr), going_right, renorm, max_bond, cutoff, mask, mom_bias, advance=False)
     if isinstance(owner, mps_lr) and not out['skipped']:
         owner.past_grad[index] = out['mean_dnll']
     if out['skipped']:
@@ -470,6 +472,20 @@ def learning_step_cached(mps, index, _imgs, lr, img_cache, going_right=True,
     tn = TensorNetwork([lt, rt])
     tn.info = out
     return tn
+
+
+def _as_array(x):
+    return x.data if isinstance(x, Tensor) else np.asarray(x)
+
+
+def _dnll_tensor(site, dn, L):
+    """dNLL as the reference hands it to update_wrap: a tensor with inds (i{k-1}, v{k}, i{k+1}, v{k+1}), rank 3 at
+    the two ends (TNutils.py:1526)."""
+    if site == 0:
+        return Tensor(dn[0], (f'v{site}', f'i{site + 1}', f'v{site + 1}'))
+    if site == L - 2:
+        return Tensor(dn[:, :, 0, :], (f'i{site - 1}', f'v{site}', f'v{site + 1}'))
+    return Tensor(dn, (f'i{site - 1}', f'v{site}', f'i{site + 1}', f'v{site + 1}'))
 
 
 def _is_identity(f):
@@ -522,12 +538,12 @@ def learning_epoch_cached(mps, *args, batch_size=25, update_wrap=None, lr_update
     eng = _ensure_capacity(mps, img_cache, max_bond)
     eng.set_mps(mps.arrays())
     owner = None
+    generic = False
     if update_wrap is not None and not _is_identity(update_wrap):
         owner = getattr(update_wrap, '__self__', None)
         if not isinstance(owner, mps_lr):
             owner = _find_mps_lr(update_wrap)
-        if owner is None:
-            raise NotImplementedError('arbitrary update_wrap callbacks are not supported by the device path')
+        generic = owner is None
     L = len(mps.tensors)
     cost = []
     lr = _copy.copy(initial_lr)
@@ -540,7 +556,11 @@ def learning_epoch_cached(mps, *args, batch_size=25, update_wrap=None, lr_update
                 np.random.shuffle(guide)
                 mask = guide[:batch_size].copy()
             mom = owner.momentum * owner.past_grad[index] if (owner is not None and owner.t > 0) else 0.0
-            out = eng.step(index, _lr_value(lr), going_right, renorm, max_bond, cutoff, mask, mom)
+            if generic:
+                out = eng.step_with_update_fn(index, _lr_value(lr), lambda site, dn: _as_array(update_wrap(site, _dnll_tensor(site, dn, L))).reshape(dn.shape),
+                                              going_right, renorm, max_bond, cutoff, mask)
+            else:
+                out = eng.step(index, _lr_value(lr), going_right, renorm, max_bond, cutoff, mask, mom)
             if owner is not None and not out['skipped']:
                 owner.past_grad[index] = out['mean_dnll']
             if index == L - 2:

@@ -213,6 +213,26 @@ class BornEngine:
         out = self.step(k, lr, going_right, **kw)
         return self.get_site(k), self.get_site(k + 1), out
 
+    def step_with_update_fn(self, k, lr, fn, going_right=True, renorm='max', max_bond=None, cutoff=1e-10, mask=None,
+                            advance=True):
+        """Two-site step with an arbitrary host-side `update_wrap(site, dNLL) -> update` (TNutils.py:1541).
+        dNLL = A/Z - S/B is formed on the host from the device results, `fn` is applied, and an equivalent
+        S' = B (A/Z - update) is uploaded so that the device update A - lr*(A/Z - S'/B) equals A - lr*update."""
+        S = self.step_grad(k, mask)
+        if self.world > 1:
+            allreduce_sum_(S, self.group)
+        B = self.N_total if mask is None else len(mask) * self.world
+        A = self.get_merged_at(k)
+        Sref = self.grad_to_ref(k, S)
+        Z = float(np.sum(A * A))
+        upd = np.asarray(fn(k, A / Z - Sref / B), dtype=np.float64)
+        S2 = np.ascontiguousarray(B * (A / Z - upd))
+        check(self._ctx, self._lib.bm_ref_to_engine(self._ctx, k, _ptr(S2), C.c_void_p(S.data_ptr())))
+        out = self.step_update(k, S, B, lr, going_right, renorm, max_bond, cutoff)
+        if advance:
+            self.env_advance(k, going_right)
+        return out
+
     def get_merged(self):
         """merged tensor A of the last step_grad, reference index order (Dl,d,Dr,d) (TNutils.py:1388)."""
         raise RuntimeError('use get_merged_at(k) right after step_grad(k)')

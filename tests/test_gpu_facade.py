@@ -184,3 +184,22 @@ def test_torched_api_flow(T, tmp_path):
     np.random.seed(10)
     c2 = T.cached_stochastic_learning_epoch(mps, imgs, _imgs, 1, 0.02, torch_cache, None, None, None, batch_size=10, max_bond=8)
     assert len(c2) == 1 and np.isfinite(c2[0])
+
+
+def test_arbitrary_update_wrap_callback(T):
+    """update_wrap(site, dNLL) with a user function (here: gradient clipping) goes through the host round trip."""
+    np.random.seed(12)
+    L, N = 8, 30
+    mps = T.initialize_mps(L, 3)
+    start = [t.copy() for t in mps.arrays()]
+    imgs = (np.random.random((N, L)) < 0.5).astype(int)
+    data = np.array([T.tens_picture(img) for img in imgs])
+    cache = T.left_right_cache(mps, data, max_bond=6)
+    seen = []
+    def clip(site, dn):
+        seen.append((site, dn.inds))
+        return dn * 0.5 if isinstance(dn, T.Tensor) else dn * 0.5
+    cost, _ = T.learning_epoch_cached(mps, imgs, data, 2, 0.1, cache, batch_size=N, update_wrap=clip, renorm='l2', max_bond=6)
+    cost_o, _ = o.learning_epoch_cached(start, imgs, 2, 0.1, renorm='l2', max_bond=6, update_wrap=lambda k, dn: 0.5 * dn)
+    np.testing.assert_allclose(cost, cost_o, rtol=1e-6)
+    assert seen[0] == (0, ('v0', 'i1', 'v1')) and seen[1][1] == ('i0', 'v1', 'i2', 'v2') and len(seen) == 2 * 2 * (L - 1)
