@@ -5,17 +5,19 @@ TEST INFRASTRUCTURE ONLY.  This module is a CPU restatement of the reference alg
 samplers.  Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference`
 legs of `bench.py` may import it; the product path (`mps_born_machines_b200`) never does.
 
-Parity pin status: PARTIALLY PINNED.
-  * Pinned against the real reference code (functions of TNutils.py that are pure numpy and can
-    be executed here with the absent third-party imports stubbed out; generator
-    `tests/golden/make_reference_golden.py`, fixtures `tests/golden/ref_*.npz`):
-    `computepsi`, `computepsiprime`, the numpy part of `learning_step` (psi'/psi accumulation),
-    `generate_sample`, `bars_n_stripes`, `partial_removal_img`, `mps_lr`.
-  * UNPINNED (restated from the published behaviour of the un-vendored dependency quimb 1.3.0,
-    which is absent from /root/reference and not installable offline): `Tensor.split`
-    (cutoff=1e-10 relative to s[0], keep >=1, cap at max_bond, no renormalisation, absorb
-    left/right), `canonize`/`right_canonize`, `MPS_rand_state`, and everything routed through
-    `tneinsum3` (batched `generate_samples`, the cached sweep).  These are validated through exact
+Parity pin status: PINNED except for the truncation rule of the un-vendored quimb `Tensor.split`.
+  * Pinned against the real reference code executed here (generators under tests/golden/, fixtures ref_*.npz):
+    - pure-numpy functions run unmodified with the absent imports stubbed (`make_reference_golden.py`):
+      `computepsi`, `computepsiprime`, the psi'/psi accumulation of `learning_step`, `generate_sample`,
+      `bars_n_stripes`, `partial_removal_img`, `mps_lr`  (psi to 4e-16, psi' and sampled bits identical);
+    - the cached (G2) path and the batched sampler run unmodified over a stand-in tensor layer
+      (`make_reference_golden_cached.py`: named-index einsum, np.linalg.svd): `tneinsum3`, `left_right_cache`,
+      `sequential_update`, `arr_psi_primed_cache`, `learning_step_cached`, `learning_epoch_cached`, `computeNLL`,
+      `generate_samples`  (float32 caches in the reference -> agreement 2e-6 on caches, 6e-6 on a 3-epoch NLL curve,
+      identical bond profile, identical 2400 sampled bits).
+  * UNPINNED: the truncation rule inside `Tensor.split` (quimb 1.3.0 defaults: cutoff=1e-10 relative to s[0], keep
+    >= 1, cap at max_bond, no renormalisation) and quimb's `canonize` / `MPS_rand_state`, restated from quimb's
+    published behaviour (quimb is absent from /root/reference and not installable offline).  Validated through exact
     linear-algebra properties and the published bars-and-stripes NLL curve
     (`notebooks/bars_n_stripes.ipynb:334-664`), a statistical pin.
 

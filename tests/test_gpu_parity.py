@@ -476,3 +476,28 @@ def test_device_canonize(bm):
         np.testing.assert_allclose(lp, lp0, rtol=1e-10)
         assert abs(np.sum(can[centre] ** 2) - o.norm2_full(raw)) < 1e-10 * o.norm2_full(raw)
     eng.close()
+
+
+def test_engine_against_reference_cached_path_golden(bm, golden_dir):
+    """the CUDA engine against vectors produced by the reference's own cached-path code (float32 caches)."""
+    f = np.load(os.path.join(golden_dir, 'ref_cached_path.npz'))
+    L = int(f['L'])
+    mps = [f[f'site{k}'] for k in range(L)]
+    imgs = f['imgs']
+    eng = engine_for(bm, mps, imgs, cap=6)
+    eng.env_build(3)
+    for j in range(0, 4):
+        np.testing.assert_allclose(eng.env_get(0, j), f[f'cacheL_{j}'], atol=2e-5)
+    for j in range(5, L + 1):
+        np.testing.assert_allclose(eng.env_get(1, j), f[f'cacheR_{j - 1}'], atol=2e-5)
+    # one teacher-forced learning_step_cached (A/A.max() renorm) : the truncated product is gauge invariant
+    out = eng.step(3, 0.05, True, 'max', max_bond=5, advance=False)
+    a, b = eng.get_site(3, squeeze=False), eng.get_site(4, squeeze=False)
+    assert out['chi'] == f['step3_left'].shape[-1]
+    np.testing.assert_allclose(np.einsum('abp,bcq->apcq', a, b), f['step3_prod'], atol=5e-5)
+    eng.close()
+    # batched sampler on the reference-trained tensors with the reference's uniforms: identical bits
+    trained = [f[f'trained{k}'] for k in range(L)]
+    eng = engine_for(bm, trained)
+    assert np.array_equal(eng.sample(f['uniforms'].shape[1], U=f['uniforms'], rule='batched'), f['samples'].astype(np.uint8))
+    eng.close()

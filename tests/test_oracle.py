@@ -216,3 +216,26 @@ def test_reconstruct_conditionals():
         z = sum(p[i] for i in compat)
         for i in compat:
             assert abs(counts.get(tuple(allimgs[i][unk]), 0) / n - p[i] / z) < 0.04
+
+
+def test_cached_path_matches_reference(golden_dir):
+    """tests/golden/make_reference_golden_cached.py: the reference's own left_right_cache / learning_step_cached /
+    learning_epoch_cached / generate_samples code (float32 caches) executed over a stand-in tensor layer."""
+    f = np.load(os.path.join(golden_dir, 'ref_cached_path.npz'))
+    L = int(f['L'])
+    mps = [f[f'site{k}'] for k in range(L)]
+    imgs = f['imgs']
+    phys = o.embed(imgs)
+    c = o.EnvCache(mps, phys, 'maxabs')
+    for j in range(L):           # img_cache[n,0,j] = left env of bond j ; img_cache[n,1,j] = right env of bond j+1
+        np.testing.assert_allclose(c.lenv[j], f[f'cacheL_{j}'], atol=2e-5)
+        np.testing.assert_allclose(c.renv[j + 1], f[f'cacheR_{j}'], atol=2e-5)
+    ref = o.two_site_step(mps, 3, c.lenv[3], c.renv[5], phys[:, 3], phys[:, 4], 0.05, True, 'max', max_bond=5)
+    assert ref['left'].shape == f['step3_left'].shape and ref['right'].shape == f['step3_right'].shape
+    np.testing.assert_allclose(np.einsum('apb,bcq->apcq', ref['left'], ref['right']), f['step3_prod'], atol=5e-5)
+    m2 = [t.copy() for t in mps]
+    cost, lr = o.learning_epoch_cached(m2, imgs, 3, 0.1, batch_size=len(imgs), max_bond=6, lr_update=lambda x: x * 0.9)
+    np.testing.assert_allclose(cost, f['epoch_cost'], rtol=5e-5)
+    assert lr == float(f['epoch_lr']) and o.bond_sizes(m2) == list(f['epoch_bonds'])
+    trained = [f[f'trained{k}'] for k in range(L)]
+    assert np.array_equal(o.generate_samples(trained, f['uniforms']), f['samples'])
