@@ -161,7 +161,7 @@ def workload_config(name, world):
     return {'workload': f'{name}: synthetic binarized 28x28 (L={L}), {N} samples total, Dmax={D}, '
                         f'mid-chain two-site steps from bond {k0} (full bond dimension), l2 renorm, cutoff 1e-10',
             'n_samples': N, 'sites': L, 'Dmax': D, 'parallelism': f'samples sharded over {world} GPU(s), '
-            'one all-reduce of the 2 MiB gradient per step, replicated SVD' if world > 1 else 'single GPU',
+            'one all-reduce of the 2 MiB gradient per step (fused into the split-reduction kernel over NVLink peer memory, or NCCL), replicated SVD' if world > 1 else 'single GPU',
             'l2': 'each step reads fresh environment slots (R slot untouched since set-up); per-step inputs '
                   '> L2 at N=1, L2 flushed between timed steps otherwise'}
 
@@ -199,6 +199,8 @@ def run_ours(args):
     eng = BornEngine(L, D, phys_dim=d, device=local, svd=args.svd, precision=args.precision)
     eng.set_data(shard, n_total=N)
     eng.set_mps(mps)
+    if world > 1 and args.allreduce == 'peer':
+        eng.enable_peer_allreduce()
     eng.env_build(start)
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
@@ -235,6 +237,7 @@ def run_ours(args):
         chis.append(out['chi'])
     barrier()
     wall = time.perf_counter() - wall0
+    step_ms = [round(a.elapsed_time(b), 3) for a, b in ev]
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = eng.launch_count() - l0
     t = torch.tensor([dev_ms], dtype=torch.float64, device=f'cuda:{local}')
@@ -311,7 +314,7 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps,
                     'd2h_bytes_per_step': d2h // steps},
             'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clk,
-            'svd': args.svd, 'chi': int(chis[-1]), 'wall_s_timed': wall, 'setup_s': t_setup,
+            'svd': args.svd, 'chi': int(chis[-1]), 'step_ms': step_ms, 'wall_s_timed': wall, 'setup_s': t_setup,
             'sweep_s_extrapolated': dev_ms / steps * 1e-3 * 2 * (L - 1),
         }
         if cpu:
@@ -401,6 +404,8 @@ def main():
     ap.add_argument('--samples', type=int, default=0)
     ap.add_argument('--svd', default='gram', choices=['gram', 'gesvdj'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
+                    help='multi-GPU gradient exchange: fused reduce + peer-memory all-reduce kernel, or NCCL')
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32'],
                     help="fp64 (default, 1e-6 parity) or tf32 (gradient accumulation on tcgen05/TMEM, 1e-3 parity)")
     ap.add_argument('--sampler-bond', type=int, default=500)

@@ -135,6 +135,14 @@ int bm_reconstruct_one(bm_ctx* ctx, const uint8_t* pixels_host, const double* u_
  * left on device.  Returns elapsed device milliseconds of the sampling loop in *ms. */
 int bm_sample_device(bm_ctx* ctx, int n, int rule, uint64_t seed, float* ms);
 
+/* Fused gradient reduction + all-reduce over NVLink peer memory (e: multi-GPU).  bm_peer_export returns the 64-byte
+ * CUDA IPC handle of this rank's exchange buffer; the host exchanges the handles of all ranks (any transport) and
+ * hands the concatenation (world x 64 bytes, rank order) to bm_peer_import.  From then on bm_step_grad delivers the
+ * gradient buffer already summed over all ranks (one kernel: local split reduction, per-chunk flag, P2P loads in
+ * rank order -> bitwise identical on every rank), and no separate collective call is needed. */
+int bm_peer_export(bm_ctx* ctx, void* handle64_out);
+int bm_peer_import(bm_ctx* ctx, const void* handles, int world, int rank);
+
 /* Per-kernel device timing for bench.py's roofline figures: when on, every hot launch is bracketed by CUDA
  * events on the context's stream (adds a host sync per launch: use it only in a measurement pass).
  * Slots: 0 env advance, 1 psi, 2 gradient, 3 gradient split-reduce, 4 merge (cuBLAS), 5 SVD (cuSOLVER),

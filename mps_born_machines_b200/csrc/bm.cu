@@ -85,6 +85,10 @@ struct bm_ctx {
   int last_kchunk = 0;
 
   Chain chain;
+  // fused reduce + all-reduce over peer memory (bm_peer_export / bm_peer_import)
+  double* peer_buf = nullptr; size_t peer_slot_elems = 0; int peer_world = 0, peer_rank = 0;
+  double* peer_base[PEER_MAX] = {nullptr}; void* peer_opened[PEER_MAX] = {nullptr};
+  unsigned long long peer_step = 0; double* tail_local = nullptr;
   // general-mask reconstruction: right-environment matrices E_j (row-major Dcap x Dcap each), vectors, counters
   double* recE = nullptr; double* recT = nullptr; double* recV[2] = {nullptr, nullptr}; double* recU = nullptr;
   uint8_t* recPix = nullptr; int* recCount = nullptr;
@@ -360,6 +364,9 @@ int bm_destroy(bm_ctx* c) {
   if (!c) return BM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (int r = 0; r < PEER_MAX; ++r) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
+  if (c->peer_buf) cudaFree(c->peer_buf);
+  if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
                   c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
@@ -659,8 +666,22 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
       if (tf32) k_grad_tf32<<<grid, TF_THREADS, sizeof(GradTf32Smem), c->stream>>>(P, c->tf_status);
       else k_grad<<<grid, GRAD_THREADS, sizeof(GradSmem), c->stream>>>(P);
     }
-    { Timer t_(c, 3); k_grad_reduce<<<148 * 4, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, S_dev); }
-    k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, S_dev + (size_t)rows * ldA);
+    if (c->peer_world > 1) {
+      // fused: local split reduction + cross-GPU sum over NVLink peer memory, straight into S_dev
+      k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, c->tail_local);
+      PeerParams PP{};
+      for (int r = 0; r < c->peer_world; ++r) {
+        PP.base[r] = c->peer_base[r];
+        PP.flags[r] = reinterpret_cast<unsigned long long*>(c->peer_base[r] + 2 * c->peer_slot_elems);
+      }
+      PP.world = c->peer_world; PP.rank = c->peer_rank; PP.step = ++c->peer_step; PP.slot = (int)(c->peer_step & 1);
+      PP.slot_elems = (long long)c->peer_slot_elems;
+      Timer t_(c, 3);
+      k_grad_reduce_peer<<<PEER_CHUNKS, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, c->tail_local, PP, S_dev, c->tf_status);
+    } else {
+      { Timer t_(c, 3); k_grad_reduce<<<148 * 4, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, S_dev); }
+      k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, S_dev + (size_t)rows * ldA);
+    }
     c->launches += 3;
     KCHECK();
   }
@@ -777,7 +798,8 @@ int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, do
   CU(cudaMemcpyAsync(c->h_scal, S_dev + (size_t)rows * ldA, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_iscal + 3, c->tf_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (c->h_iscal[3] != 0) return fail(c, BM_ECUDA, "k_grad_tf32: mbarrier wait timed out (tcgen05 pipeline)");
+  if (c->h_iscal[3] == 1) return fail(c, BM_ECUDA, "k_grad_tf32: mbarrier wait timed out (tcgen05 pipeline)");
+  if (c->h_iscal[3] == 2) return fail(c, BM_ECUDA, "k_grad_reduce_peer: a peer rank did not publish its gradient chunk (flag wait timed out)");
   const double sumln = c->h_scal[0], nzero = c->h_scal[1];
   if (nzero > 0) {
     if (scalars_host) { std::memset(scalars_host, 0, 8 * sizeof(double)); scalars_host[1] = sumln; scalars_host[2] = nzero; }
@@ -1061,6 +1083,47 @@ int bm_reconstruct_one(bm_ctx* c, const uint8_t* pixels_host, const double* u_ho
   KCHECK();
   CU(cudaMemcpyAsync(out_host, c->recPix, L, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return BM_OK;
+}
+
+// ---- fused reduce + all-reduce over peer memory ----------------------------------------------------------------
+// bm_peer_export: allocate this rank's shared buffer (2 slots of [S | 2 scalars] + flags) and return its CUDA IPC handle
+// (64 bytes).  The caller exchanges the handles of all ranks (e.g. torch.distributed.all_gather_object) and passes
+// them to bm_peer_import, which maps the peers.  After that bm_step_grad returns the ALL-REDUCED buffer directly.
+int bm_peer_export(bm_ctx* c, void* handle64_out) {
+  if (!c || !handle64_out) return BM_EINVAL;
+  CU(cudaSetDevice(c->device));
+  const size_t mA = (size_t)c->d * c->Dcap, ldA = (size_t)c->d * c->ldcap;
+  c->peer_slot_elems = mA * ldA + 2;
+  REQUIRE(c->peer_slot_elems <= (size_t)PEER_CHUNKS * 1024, "bm_peer_export: gradient too large for the fused peer kernel (use the NCCL path)");
+  const size_t flag_doubles = 2 * (size_t)PEER_CHUNKS;     // uint64 flags occupy the same 8 bytes as a double
+  if (!c->peer_buf) {
+    DALLOC(c->peer_buf, 2 * c->peer_slot_elems + flag_doubles);
+    CU(cudaMemset(c->peer_buf, 0, (2 * c->peer_slot_elems + flag_doubles) * sizeof(double)));
+    DALLOC(c->tail_local, 2);
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->peer_buf));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::memcpy(handle64_out, &h, 64);
+  return BM_OK;
+}
+
+int bm_peer_import(bm_ctx* c, const void* handles, int world, int rank) {
+  if (!c || !handles) return BM_EINVAL;
+  REQUIRE(world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world, "bm_peer_import: bad world / rank");
+  REQUIRE(c->peer_buf, "bm_peer_import: call bm_peer_export first");
+  CU(cudaSetDevice(c->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { c->peer_base[r] = c->peer_buf; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_opened[r] = p;
+    c->peer_base[r] = (double*)p;
+  }
+  c->peer_world = world; c->peer_rank = rank; c->peer_step = 0;
   return BM_OK;
 }
 

@@ -751,6 +751,91 @@ __global__ void k_grad_reduce(const double* __restrict__ ws, long long ws_stride
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused split reduction + cross-GPU all-reduce over NVLink peer memory (one launch, replaces k_grad_reduce + NCCL).
+//   Every rank runs the same grid.  CTA c owns chunk c of the buffer [ S | sum ln|psi| | #zero psi ]:
+//     1. sums its chunk over the local sample splits (fixed order) and publishes it in this rank's IPC-shared slot,
+//     2. __threadfence_system + release-store of flag[rank][slot][c] = step,
+//     3. acquires flag[p][slot][c] == step of every peer p (bounded spin: a missing rank raises status, never hangs),
+//     4. sums the chunk over ranks 0..world-1 in rank order with P2P loads (own part from registers) -> S_out.
+//   No CTA waits on another CTA of its own grid, so no co-residency requirement; results are bitwise identical on all
+//   ranks (same summation order), which keeps the replicated split in lock-step.  Slots alternate per step: a slot is
+//   rewritten at step s+2, after every peer has finished step s (they had to publish step s+1 first).
+// ------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX = 8;
+constexpr int PEER_CHUNKS = 592;          // 148 SMs x 4
+struct PeerParams {
+  double* base[PEER_MAX];                 // IPC-mapped buffers: [2 slots][slot_elems] doubles, then flags
+  unsigned long long* flags[PEER_MAX];    // [2 slots][PEER_CHUNKS]
+  int world, rank, slot;
+  unsigned long long step;
+  long long slot_elems;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_grad_reduce_peer(const double* __restrict__ ws, long long ws_stride, const int* __restrict__ goff,
+                                                          int kchunk, int d, int Dl, int Dr, int ldA, int ldRpad,
+                                                          const double* __restrict__ tail_local, PeerParams PP,
+                                                          double* __restrict__ S_out, int* __restrict__ status) {
+  const long long nS = (long long)d * Dl * ldA, total = nS + 2;
+  const long long per = (total + PEER_CHUNKS - 1) / PEER_CHUNKS;
+  const int c = blockIdx.x;
+  const long long e0 = (long long)c * per, e1 = e0 + per < total ? e0 + per : total;
+  constexpr int MAXE = 4;                                   // elements per thread (per <= 1024 for 512 x 512 + 2)
+  double mine[MAXE];
+  double* my = PP.base[PP.rank] + (long long)PP.slot * PP.slot_elems;
+#pragma unroll
+  for (int j = 0; j < MAXE; ++j) {
+    const long long e = e0 + threadIdx.x + (long long)j * 256;
+    double s = 0.0;
+    if (e < e1) {
+      if (e < nS) {
+        int row = (int)(e / ldA), col = (int)(e % ldA);
+        int p = row / Dl, q = col / ldRpad, cc = col % ldRpad;
+        if (cc < Dr && q < d) {
+          int g = p * d + q;
+          int ns = (goff[g + 1] - goff[g] + kchunk - 1) / kchunk;
+          for (int i = 0; i < ns; ++i) s += ws[(long long)i * ws_stride + e];
+        }
+      } else s = tail_local[e - nS];
+      my[e] = s;
+    }
+    mine[j] = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(PP.flags[PP.rank] + (long long)PP.slot * PEER_CHUNKS + c, PP.step);
+  __shared__ int ok_s;
+  if (threadIdx.x == 0) ok_s = 1;
+  __syncthreads();
+  if (threadIdx.x < PP.world && threadIdx.x != PP.rank) {
+    const unsigned long long* f = PP.flags[threadIdx.x] + (long long)PP.slot * PEER_CHUNKS + c;
+    bool ok = false;
+    for (long long it = 0; it < (1LL << 23); ++it) { if (ld_acquire_sys(f) == PP.step) { ok = true; break; } }
+    if (!ok) { ok_s = 0; atomicExch(status, 2); }
+  }
+  __syncthreads();
+  if (!ok_s) return;
+#pragma unroll
+  for (int j = 0; j < MAXE; ++j) {
+    const long long e = e0 + threadIdx.x + (long long)j * 256;
+    if (e < e1) {
+      double s = 0.0;
+      for (int p = 0; p < PP.world; ++p)
+        s += (p == PP.rank) ? mine[j] : __ldcv(PP.base[p] + (long long)PP.slot * PP.slot_elems + e);
+      S_out[e] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // sampler step (one site, all samples)
 // ------------------------------------------------------------------------------------------------
 struct SampleParams {

@@ -49,10 +49,30 @@ class BornEngine:
         self._S = torch.zeros(self.d * self.Dcap * self.d * ld + 2, dtype=torch.float64, device=f'cuda:{self.device}')
         self.N = 0
         self.N_total = 0
+        self.peer = False
         self.group = dist_group
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(dist_group)
+
+    def enable_peer_allreduce(self):
+        """Switch the per-step gradient all-reduce from NCCL to the fused peer-memory kernel (k_grad_reduce_peer):
+        exchanges CUDA IPC handles of the per-rank exchange buffers once; afterwards step_grad returns the
+        already all-reduced buffer and step() issues no collective."""
+        if self.world <= 1:
+            return False
+        import torch.distributed as dist
+        h = (C.c_char * 64)()
+        check(self._ctx, self._lib.bm_peer_export(self._ctx, h))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(h.raw), group=self.group)
+        blob = b''.join(gathered)
+        rank = dist.get_rank(self.group)
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        check(self._ctx, self._lib.bm_peer_import(self._ctx, buf, self.world, rank))
+        dist.barrier(group=self.group)
+        self.peer = True
+        return True
 
     def close(self):
         if getattr(self, '_ctx', None) is not None and self._ctx.value:
@@ -173,8 +193,8 @@ class BornEngine:
              want_s=False, batch_total=None, advance=True):
         """One learning_step_cached + write-back + sequential_update (TNutils.py:1603-1620)."""
         S = self.step_grad(k, mask)
-        if self.world > 1:
-            allreduce_sum_(S, self.group)   # sum over sample shards (NCCL over NVLink)
+        if self.world > 1 and not self.peer:
+            allreduce_sum_(S, self.group)   # sum over sample shards (NCCL over NVLink); peer mode: already reduced in-kernel
         if batch_total is None:
             batch_total = self.N_total if mask is None else len(mask) * self.world
         out = self.step_update(k, S, batch_total, lr, going_right, renorm, max_bond, cutoff, mom_bias, want_s)
@@ -219,7 +239,7 @@ class BornEngine:
         dNLL = A/Z - S/B is formed on the host from the device results, `fn` is applied, and an equivalent
         S' = B (A/Z - update) is uploaded so that the device update A - lr*(A/Z - S'/B) equals A - lr*update."""
         S = self.step_grad(k, mask)
-        if self.world > 1:
+        if self.world > 1 and not self.peer:
             allreduce_sum_(S, self.group)
         B = self.N_total if mask is None else len(mask) * self.world
         A = self.get_merged_at(k)

@@ -28,6 +28,9 @@ mps = mpslib.random_mps(L, 4, rng=np.random.default_rng(1), centre=0)
 lo, hi = shard_bounds(N, world, rank)
 eng = BornEngine(L, D, device=local)
 eng.set_mps(mps); eng.set_data(imgs[lo:hi], n_total=N)
+PEER = '--peer' in sys.argv
+if PEER:
+    assert eng.enable_peer_allreduce()
 single = None
 if rank == 0:
     single = BornEngine(L, D, device=local)
@@ -51,7 +54,7 @@ for i, k in enumerate(sweep_schedule(L)):
 drift = max(replicated_checksum(torch.from_numpy(t).cuda()) for t in eng.get_mps())
 nll = eng.nll(imgs, 0)
 if rank == 0:
-    print(f'multi-GPU check: world={world}, {2 * (L - 1)} teacher-forced steps: max rel diff singular values {worst_s:.2e}, '
+    print(f'multi-GPU check ({"fused peer-memory all-reduce" if PEER else "NCCL all-reduce"}): world={world}, {2 * (L - 1)} teacher-forced steps: max rel diff singular values {worst_s:.2e}, '
           f'sum ln|psi| {worst_ln:.2e}, Z {worst_z:.2e}; replica drift {drift:.1e}; NLL after sweep {nll:.6f}')
     ok = ok and worst_s < 1e-6 and worst_ln < 1e-9 and worst_z < 1e-9 and drift == 0.0
     print('MULTI_GPU_CHECK', 'OK' if ok else 'FAILED')
