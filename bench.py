@@ -199,8 +199,12 @@ def run_ours(args):
     eng = BornEngine(L, D, phys_dim=d, device=local, svd=args.svd, precision=args.precision)
     eng.set_data(shard, n_total=N)
     eng.set_mps(mps)
+    allreduce_mode = 'none' if world == 1 else args.allreduce
     if world > 1 and args.allreduce == 'peer':
-        eng.enable_peer_allreduce()
+        try:
+            eng.enable_peer_allreduce()
+        except Exception as exc:          # e.g. CUDA IPC unavailable in this container: fall back to NCCL, say so
+            allreduce_mode = f'nccl (peer-memory path unavailable: {exc})'
     eng.env_build(start)
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
@@ -314,7 +318,7 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps,
                     'd2h_bytes_per_step': d2h // steps},
             'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clk,
-            'svd': args.svd, 'chi': int(chis[-1]), 'step_ms': step_ms, 'wall_s_timed': wall, 'setup_s': t_setup,
+            'svd': args.svd, 'allreduce': allreduce_mode, 'chi': int(chis[-1]), 'step_ms': step_ms, 'wall_s_timed': wall, 'setup_s': t_setup,
             'sweep_s_extrapolated': dev_ms / steps * 1e-3 * 2 * (L - 1),
         }
         if cpu:
