@@ -62,15 +62,30 @@ class BornEngine:
         if self.world <= 1:
             return False
         import torch.distributed as dist
-        h = (C.c_char * 64)()
-        check(self._ctx, self._lib.bm_peer_export(self._ctx, h))
+        ok, err = 1, None
+        try:
+            h = (C.c_char * 64)()
+            check(self._ctx, self._lib.bm_peer_export(self._ctx, h))
+            payload = bytes(h.raw)
+        except Exception as exc:      # keep going: the outcome must be agreed on by ALL ranks
+            ok, err, payload = 0, exc, b'\0' * 64
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, bytes(h.raw), group=self.group)
-        blob = b''.join(gathered)
+        dist.all_gather_object(gathered, payload, group=self.group)
         rank = dist.get_rank(self.group)
-        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
-        check(self._ctx, self._lib.bm_peer_import(self._ctx, buf, self.world, rank))
-        dist.barrier(group=self.group)
+        if ok:
+            try:
+                blob = b''.join(gathered)
+                buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+                check(self._ctx, self._lib.bm_peer_import(self._ctx, buf, self.world, rank))
+            except Exception as exc:
+                ok, err = 0, exc
+        flag = torch.tensor([ok], dtype=torch.int32, device=f'cuda:{self.device}')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:     # some rank could not map its peers: everybody stays on the NCCL path
+            one = (C.c_char * 64)()
+            self._lib.bm_peer_import(self._ctx, one, 1, 0)
+            self.peer = False
+            raise RuntimeError(f'peer-memory all-reduce unavailable on at least one rank ({err})')
         self.peer = True
         return True
 
