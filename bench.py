@@ -303,6 +303,20 @@ def run_ours(args):
                                f'MEASURED_PEAKS.json {peak_src}',
                 'algorithmic_flops_per_launch': 2.0 * D * D * n_loc, 'kernels': ker}
 
+    # ---- secondary metric of BASELINE.json: samples generated / s (batched ancestral sampler, device-resident).
+    #      Reuses this engine: the chain right of the current centre is right-canonical, and the sampler's arithmetic
+    #      and cost do not depend on the gauge of the left part (the full config-4 run is `--workload c4`).
+    sampler = None
+    if world == 1 and not args.no_sampler:
+        ns = 20000
+        eng.sample_device_ms(2048, seed=3)
+        ms_s = [eng.sample_device_ms(ns, seed=7 + i) for i in range(2)]
+        sampler = {'metric': 'samples_generated_per_s', 'value': ns / (min(ms_s) * 1e-3), 'unit': 'samples/s',
+                   'n_samples': ns, 'sites': L, 'Dmax': D, 'ms': min(ms_s),
+                   'tflops_executed': 2.0 * D * D * 2.0 * L * ns / (min(ms_s) * 1e-3) / 1e12,
+                   'note': 'generate_samples (TNutils.py:1829) on the bench MPS, uniforms generated on device; config 4 '
+                           '(D=500, N=100k): python bench.py --workload c4 -> 34.5k samples/s (profiles/r01_bench_c4_sampler.json)'}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -323,6 +337,8 @@ def run_ours(args):
         }
         if cpu:
             line['cpu_baseline'] = cpu
+        if sampler:
+            line['sampler'] = sampler
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -408,6 +424,7 @@ def main():
     ap.add_argument('--samples', type=int, default=0)
     ap.add_argument('--svd', default='gram', choices=['gram', 'gesvdj'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-sampler', action='store_true', help='skip the secondary samples/s measurement')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
                     help='multi-GPU gradient exchange: fused reduce + peer-memory all-reduce kernel, or NCCL')
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32'],
