@@ -38,7 +38,9 @@ enum {
 };
 
 enum { BM_RENORM_MAX = 0 /* A/A.max(), TNutils.py:1542 */, BM_RENORM_L2 = 1 /* A/sqrt(A.A), :1419,:1257 */ };
-enum { BM_SVD_GESVDJ = 0, BM_SVD_GESVD = 1, BM_SVD_GRAM = 2 };
+enum { BM_SVD_GESVDJ = 0, BM_SVD_GESVD = 1,
+       BM_SVD_GRAM = 2 /* Gram split; on-chip eigensolver where it applies, cuSOLVER syevd otherwise */,
+       BM_SVD_GRAM_SYEVD = 3 /* Gram split, cuSOLVER syevd only */ };
 enum { BM_RULE_BATCHED = 0 /* generate_samples: u <= P(pixel 1), :1840,:1853 */,
        BM_RULE_SINGLE = 1  /* generate_sample: u <  P(pixel 0), :1950,:1972,:1990 */ };
 
@@ -50,6 +52,14 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
 int bm_destroy(bm_ctx* ctx);
 const char* bm_last_error(bm_ctx* ctx);
 int bm_set_svd(bm_ctx* ctx, int method);
+/* Eigen-decomposition of a symmetric n x n host matrix (column-major) with the engine's eigensolvers: the factorisation
+ * inside `Tensor.split` (TNutils.py:1552-1564; quimb -> LAPACK in the reference).  on_chip = 1: cluster
+ * tridiagonalisation + multisection + twisted factorisation (n <= 512), 0: cuSOLVER syevd.  lam_host[n] ascending;
+ * U_host (n x m) = eigenvectors of the m largest, descending; info8 = {device ms, max|U^T U - I| before the polish, on_chip,
+ * stage ms: tridiagonalisation, eigenvalues, readback+twisted vectors, back-transformation, polish}. */
+int bm_eig_sym(bm_ctx* ctx, int n, const double* G_host, int m, int on_chip, double* lam_host, double* U_host, double* info8);
+/* how many splits ran on the on-chip eigensolver / fell back to cuSOLVER (degenerate or rank-deficient spectra) */
+int bm_eig_stats(bm_ctx* ctx, long long* on_chip, long long* fallback);
 /* grad_tf32 = 1: accumulate S = sum psi'/psi with tcgen05.mma.kind::tf32 into TMEM (1e-3 parity class; bonds <= 256,
  * larger bonds fall back to the FP64 DMMA kernel).  psi, environments, update and split stay FP64. */
 int bm_set_precision(bm_ctx* ctx, int grad_tf32);

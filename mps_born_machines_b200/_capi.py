@@ -8,7 +8,7 @@ LIB_PATH = os.environ.get('BM_LIB_PATH') or os.path.join(HERE, '_lib', 'libbm.so
 
 BM_OK, BM_EINVAL, BM_ECUDA, BM_ECUSOLVER, BM_EZERO_PSI, BM_ENONFINITE, BM_ENOMEM = range(7)
 RENORM = {'max': 0, 'l2': 1}
-SVD = {'gesvdj': 0, 'gesvd': 1, 'gram': 2}
+SVD = {'gesvdj': 0, 'gesvd': 1, 'gram': 2, 'gram_syevd': 3}
 RULE = {'batched': 0, 'single': 1}
 
 # every symbol include/bm.h declares: (name, restype, argtypes)
@@ -19,6 +19,8 @@ _SIGS = [
     ('bm_destroy', C.c_int, [_P]),
     ('bm_last_error', C.c_char_p, [_P]),
     ('bm_set_svd', C.c_int, [_P, C.c_int]),
+    ('bm_eig_sym', C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
+    ('bm_eig_stats', C.c_int, [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     ('bm_set_precision', C.c_int, [_P, C.c_int]),
     ('bm_set_data', C.c_int, [_P, _P, C.c_int]),
     ('bm_set_site', C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int]),

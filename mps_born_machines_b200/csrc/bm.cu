@@ -4,6 +4,7 @@
 #include <cusolverDn.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +13,7 @@
 
 #include "../../include/bm.h"
 #include "bm_kernels.cuh"
+#include "bm_eig.cuh"
 
 using namespace bm;
 
@@ -75,6 +77,14 @@ struct bm_ctx {
   double* h_lam = nullptr;   // pinned
   std::vector<double> h_s;
   int gram_levels = 0;
+  // on-chip symmetric eigensolver (bm_eig.cuh): tridiagonal (eD,eE), reflectors (eTau,eV), twisted-factorisation
+  // work arrays eW[4], tridiagonal eigenvectors eZ, 1/norms eZn, polish matrix eC, deviation eDev
+  int eig_ok = 0;            // a 16-CTA cluster can be launched on this device
+  double *eD = nullptr, *eE = nullptr, *eTau = nullptr, *eV = nullptr, *eW = nullptr, *eZ = nullptr, *eZn = nullptr,
+         *eC = nullptr, *eDev = nullptr, *eLam = nullptr;
+  double* h_dev = nullptr;   // pinned
+  long long eig_fast = 0, eig_fallback = 0;
+  int eig_prof = 0; cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; float eig_ms[5] = {0, 0, 0, 0, 0};
   int* info = nullptr; int* iscal = nullptr;
   double *psi = nullptr, *winv = nullptr, *lnpsi = nullptr;
   double* ws = nullptr; int ws_slots = 0;
@@ -180,6 +190,70 @@ int set_func_attrs(bm_ctx* c) {
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_psi, NTHREADS, PANEL_SMEM));
   c->panel_ctas = std::max(1, occ) * c->n_sm;
+  return BM_OK;
+}
+
+
+// ---- on-chip symmetric eigensolver (bm_eig.cuh) -----------------------------------------------------------------
+int eig_setup(bm_ctx* c) {
+  c->eig_ok = 0;
+  if (cudaFuncSetAttribute(k_sytrd_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return BM_OK;                 // no 16-CTA clusters on this device: cuSOLVER path only
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(EIG_CL); cfg.blockDim = dim3(EIG_NT); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = EIG_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, k_sytrd_cluster, &cfg) != cudaSuccess) { cudaGetLastError(); return BM_OK; }
+  if (ncl < 1) return BM_OK;
+  const size_t N = EIG_NMAX;
+  DALLOC(c->eD, N); DALLOC(c->eE, N); DALLOC(c->eTau, N); DALLOC(c->eLam, N); DALLOC(c->eZn, N); DALLOC(c->eDev, 2);
+  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eW, 4 * N * N); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N);
+  CU(cudaMallocHost((void**)&c->h_dev, 2 * sizeof(double)));
+  c->eig_ok = 1;
+  return BM_OK;
+}
+
+// eigenvalues of the symmetric n x n matrix G (device, ld) -> c->eLam (device, ascending).  Reflectors stay in eV/eTau.
+int eig_values(bm_ctx* c, const double* G, int ld, int n) {
+  if (c->eig_prof) cudaEventRecord(c->eig_ev[0], c->stream);
+  k_sytrd_cluster<<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV);
+  if (c->eig_prof) cudaEventRecord(c->eig_ev[1], c->stream);
+  k_tri_eigvals<<<(n + EIGV_WARPS - 1) / EIGV_WARPS, EIGV_WARPS * 32, 0, c->stream>>>(c->eD, c->eE, n, c->eLam);
+  if (c->eig_prof) cudaEventRecord(c->eig_ev[2], c->stream);
+  c->launches += 2;
+  KCHECK();
+  return BM_OK;
+}
+
+// eigenvectors of the m largest eigenvalues (descending) -> U (n x m, ldu), one Newton-Schulz polish; h_dev[0] =
+// max |U^T U - I| BEFORE the polish (the result deviates by its square).  Synchronises the stream.
+int eig_vectors(bm_ctx* c, int n, int m, double* U, int ldu) {
+  const size_t NN = (size_t)EIG_NMAX * EIG_NMAX;
+  k_tri_vectors<<<(m + 31) / 32, 64, 0, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eW, c->eW + NN, c->eW + 2 * NN, c->eW + 3 * NN, c->eZ, c->eZn);
+  if (c->eig_prof) cudaEventRecord(c->eig_ev[3], c->stream);
+  k_apply_reflectors<<<(m + REFL_WARPS - 1) / REFL_WARPS, REFL_WARPS * 32, 0, c->stream>>>(c->eV, c->eTau, n, c->eZ, c->eZn, m, U, ldu);
+  if (c->eig_prof) cudaEventRecord(c->eig_ev[4], c->stream);
+  c->launches += 2;
+  KCHECK();
+  const double one = 1.0, zero = 0.0;
+  c->h_dev[0] = c->h_dev[1] = DBL_MAX;
+  for (int round = 0; round < 2; ++round) {
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, m, m, n, &one, U, ldu, U, ldu, &zero, c->eC, m));
+    k_polish_coef<<<1, 1024, 0, c->stream>>>(c->eC, m, m, c->eDev + round);
+    c->launches++;
+    KCHECK();
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, n, m, m, &one, U, ldu, c->eC, m, &zero, c->eZ, n));
+    CU(cudaMemcpy2DAsync(U, (size_t)ldu * sizeof(double), c->eZ, (size_t)n * sizeof(double), (size_t)n * sizeof(double), m, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->h_dev + round, c->eDev + round, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (round == 0 && c->h_dev[0] < 1e-8) break;      // deviation after the polish ~ square of it: done
+    if (round == 0 && !(c->h_dev[0] < 1e-3)) break;   // hopeless (degenerate cluster / NaN): caller falls back
+  }
   return BM_OK;
 }
 
@@ -353,6 +427,8 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
   DALLOC(c->Gq, mA * mA); DALLOC(c->Yb[0], mA * mA); DALLOC(c->Yb[1], mA * mA); DALLOC(c->Tb[0], mA * mA); DALLOC(c->Tb[1], mA * mA);
   DALLOC(c->Tmp, mA * mA); DALLOC(c->lam, mA);
   CU(cudaMallocHost((void**)&c->h_lam, (mA + 2) * sizeof(double)));
+  r = eig_setup(c);
+  if (r != BM_OK) return r;
   DALLOC(c->partZ, RED_BLOCKS); DALLOC(c->part2, RED_BLOCKS * 4); DALLOC(c->scal, 8);
   CU(cudaMallocHost((void**)&c->h_scal, 8 * sizeof(double)));
   CU(cudaMallocHost((void**)&c->h_iscal, 4 * sizeof(int)));
@@ -368,7 +444,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eW, c->eZ, c->eZn, c->eC, c->eDev, c->eLam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -376,6 +452,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->h_iscal) cudaFreeHost(c->h_iscal);
   if (c->h_lam) cudaFreeHost(c->h_lam);
+  if (c->h_dev) cudaFreeHost(c->h_dev);
   if (c->tev[0]) { cudaEventDestroy(c->tev[0]); cudaEventDestroy(c->tev[1]); }
   if (c->gesvdj) cusolverDnDestroyGesvdjInfo(c->gesvdj);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
@@ -399,6 +476,70 @@ int bm_get_timing(bm_ctx* c, double* ms8, long long* n8) {
   return BM_OK;
 }
 
+// Symmetric eigen-decomposition of a host matrix on the device (test / inspection entry for bm_eig.cuh).
+int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, double* lam_host, double* U_host, double* info3) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(G_host && lam_host && n >= 1 && m >= 0 && m <= n, "bm_eig_sym: bad arguments");
+  const int cap = c->d * c->Dcap;
+  REQUIRE(n <= cap, "bm_eig_sym: n exceeds phys_dim * max_bond_cap of this context");
+  REQUIRE(!on_chip || (c->eig_ok && n <= EIG_NMAX && n >= 2), "bm_eig_sym: on-chip eigensolver not available for this size/device");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->Gq, G_host, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, c->stream));
+  double dev0 = 0.0;
+  if (on_chip) {
+    if (!c->eig_ev[0]) for (auto& ev : c->eig_ev) CU(cudaEventCreate(&ev));
+    c->eig_prof = 1;
+    int r = eig_values(c, c->Gq, n, n);
+    c->eig_prof = m > 0;
+    if (r != BM_OK) return r;
+    CU(cudaMemcpyAsync(lam_host, c->eLam, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (m > 0) {
+      r = eig_vectors(c, n, m, c->Tmp, n);
+      if (r != BM_OK) return r;
+      dev0 = c->h_dev[0];
+    }
+  } else {
+    int lw = 0;
+    LIB(cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, c->Gq, n, c->lam, &lw));
+    if ((size_t)lw > c->lwork) { DALLOC(c->work, (size_t)lw); c->lwork = (size_t)lw; }
+    LIB(cusolverDnDsyevd(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, c->Gq, n, c->lam, c->work, lw, c->info));
+    CU(cudaMemcpyAsync(lam_host, c->lam, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (m > 0) {
+      k_cols_reverse_copy<<<148, 256, 0, c->stream>>>(c->Gq + (size_t)(n - m) * n, n, n, m, c->Tmp, n);
+      c->launches++;
+      KCHECK();
+    }
+  }
+  CU(cudaEventRecord(e1, c->stream));
+  if (m > 0 && U_host) CU(cudaMemcpyAsync(U_host, c->Tmp, (size_t)n * m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  if (info3) { info3[0] = ms; info3[1] = dev0; info3[2] = on_chip ? 1.0 : 0.0; }
+  if (info3 && on_chip) {   // stage times: tridiagonalisation, eigenvalues, (gap), twisted vectors, back-transformation
+    float f = 0.f;
+    cudaEventElapsedTime(&f, c->eig_ev[0], c->eig_ev[1]); info3[3] = f;
+    cudaEventElapsedTime(&f, c->eig_ev[1], c->eig_ev[2]); info3[4] = f;
+    if (m > 0) {
+      cudaEventElapsedTime(&f, c->eig_ev[2], c->eig_ev[3]); info3[5] = f;
+      cudaEventElapsedTime(&f, c->eig_ev[3], c->eig_ev[4]); info3[6] = f;
+      cudaEventElapsedTime(&f, c->eig_ev[4], e1); info3[7] = f;
+    }
+  }
+  c->eig_prof = 0;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return BM_OK;
+}
+
+int bm_eig_stats(bm_ctx* c, long long* on_chip, long long* fallback) {
+  if (!c || !on_chip || !fallback) return BM_EINVAL;
+  *on_chip = c->eig_fast; *fallback = c->eig_fallback;
+  return BM_OK;
+}
+
 int bm_set_precision(bm_ctx* c, int grad_tf32) {
   if (!c) return BM_EINVAL;
   c->grad_tf32 = grad_tf32 ? 1 : 0;
@@ -407,7 +548,7 @@ int bm_set_precision(bm_ctx* c, int grad_tf32) {
 
 int bm_set_svd(bm_ctx* c, int method) {
   if (!c) return BM_EINVAL;
-  REQUIRE(method == BM_SVD_GESVDJ || method == BM_SVD_GRAM, "unsupported SVD method");
+  REQUIRE(method == BM_SVD_GESVDJ || method == BM_SVD_GRAM || method == BM_SVD_GRAM_SYEVD, "unsupported SVD method");
   c->svd_method = method;
   return BM_OK;
 }
@@ -720,6 +861,55 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
   const double* T = nullptr;
   int pl = p, lev = 0, yb = 0, tb = 0, ncols_out = 0;
   double sigma0sq = 0.0;
+  // ---- fast path: on-chip eigensolver (bm_eig.cuh).  Applies when one Gram level resolves every kept singular value
+  // (all above sqrt(TAU) s_0) and the kept eigenvalues are separated well enough for twisted-factorisation vectors;
+  // otherwise (rank-deficient / degenerate spectra, n > 512) the cuSOLVER levels below run unchanged.
+  if (c->svd_method == BM_SVD_GRAM && c->eig_ok && p <= EIG_NMAX && p >= 2) {
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, p, p, q, &one, c->W, q, c->W, q, &zero, c->Gq, p));
+    int r = eig_values(c, c->Gq, p, p);
+    if (r != BM_OK) return r;
+    CU(cudaMemcpyAsync(c->h_lam, c->eLam, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double* lam = c->h_lam;
+    const double lmax = lam[p - 1];
+    bool ok = lmax > 0.0 && std::isfinite(lmax);
+    int kkeep = 0;
+    if (ok) while (kkeep < p && lam[p - 1 - kkeep] > TAU * lmax) ++kkeep;
+    ok = ok && (kkeep >= need || kkeep == p);
+    int chi = 0;
+    if (ok) {
+      sv.resize(p);
+      for (int j = 0; j < p; ++j) sv[j] = std::sqrt(std::max(lam[p - 1 - j], 0.0));
+      if ((int)sv.size() > rmin) sv.resize(rmin);
+      if (cutoff > 0.0) {
+        for (double x : sv) if (x > cutoff * sv[0]) ++chi;
+        chi = std::max(chi, 1);
+        if (max_bond > 0) chi = std::min(chi, max_bond);
+      } else chi = max_bond > 0 ? std::min(max_bond, (int)sv.size()) : (int)sv.size();
+      ok = chi <= kkeep;
+      // separation of the kept eigenvalues (and of the last kept one from the first discarded one)
+      double gap = DBL_MAX;
+      for (int j = 0; j < chi && j + 1 < p; ++j) gap = std::min(gap, lam[p - 1 - j] - lam[p - 2 - j]);
+      ok = ok && (gap > 4.0 * DBL_EPSILON * lmax * 1e5);     // predicted loss of orthogonality below 1e-5
+    }
+    if (ok) {
+      r = eig_vectors(c, p, chi, iso, p);
+      if (r != BM_OK) return r;
+      const double devn = c->h_dev[0] < 1e-8 ? c->h_dev[0] * c->h_dev[0] : c->h_dev[1] * c->h_dev[1];
+      ok = devn < 1e-13;
+    }
+    if (ok) {
+      c->eig_fast++;
+      c->gram_levels = 1;
+      double t2 = 0.0;
+      for (size_t i = chi; i < sv.size(); ++i) t2 += sv[i] * sv[i];
+      *chi_out = chi; *trunc_out = std::sqrt(t2);
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, q, chi, p, &one, c->W, q, iso, p, &zero, absb, q));
+      return BM_OK;
+    }
+    c->eig_fallback++;
+    sv.clear();
+  }
   while (true) {
     ++lev;
     LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, pl, pl, q, &one, Yl, q, Yl, q, &zero, c->Gq, pl));
@@ -816,7 +1006,7 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, double batch_total
   const int Dl = c->sDl[k], Dr = c->sDr[k + 1];
   const int ldr = even(Dr), ldA = d * ldr, rows = d * Dl, ncols = d * Dr;
   const int rmin = std::min(rows, ncols);
-  const bool gram = c->svd_method == BM_SVD_GRAM;
+  const bool gram = c->svd_method == BM_SVD_GRAM || c->svd_method == BM_SVD_GRAM_SYEVD;
   k_update<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, S_dev, c->partZ, rows, ldA, Dr, ldr, batch_total, lr, mom_bias, c->A2, c->part2, c->scal);
   k_scale_to_colmajor<<<RED_BLOCKS * 4, 256, 0, c->stream>>>(c->A2, c->part2, rows, ldA, d, Dr, ldr, renorm,
                                                              (gram && going_right) ? 1 : 0, c->W, c->scal);

@@ -375,6 +375,26 @@ class BornEngine:
     def launch_count(self):
         return int(self._lib.bm_launch_count(self._ctx))
 
+    def eig_sym(self, G, m=None, on_chip=True):
+        """Eigen-decomposition of a symmetric matrix with the split's eigensolver (`bm_eig_sym`).
+        Returns (lam ascending, U = eigenvectors of the m largest in descending order, info dict)."""
+        G = np.asfortranarray(G, dtype=np.float64)
+        n = G.shape[0]
+        m = n if m is None else int(m)
+        lam = np.empty(n)
+        U = np.empty((n, m), order='F')
+        info = np.zeros(8)
+        check(self._ctx, self._lib.bm_eig_sym(self._ctx, n, G.ctypes.data, m, int(bool(on_chip)), lam.ctypes.data,
+                                              U.ctypes.data, info.ctypes.data))
+        return lam, U, {'ms': info[0], 'ortho_dev': info[1], 'on_chip': bool(info[2]),
+                        'stage_ms': dict(zip(('sytrd', 'eigvals', 'vectors', 'reflectors', 'polish'), info[3:8].tolist()))}
+
+    def eig_stats(self):
+        """(splits that ran on the on-chip eigensolver, splits that fell back to cuSOLVER syevd)"""
+        a, b = C.c_longlong(), C.c_longlong()
+        check(self._ctx, self._lib.bm_eig_stats(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
 
 def uniforms_reference(seed, site, n):
     """Host mirror of the device generator k_fill_uniform (splitmix64 counter hash)."""

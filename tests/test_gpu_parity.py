@@ -501,3 +501,71 @@ def test_engine_against_reference_cached_path_golden(bm, golden_dir):
     eng = engine_for(bm, trained)
     assert np.array_equal(eng.sample(f['uniforms'].shape[1], U=f['uniforms'], rule='batched'), f['samples'].astype(np.uint8))
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# on-chip symmetric eigensolver of the Gram split (bm_eig.cuh) against LAPACK
+# ------------------------------------------------------------------------------------------------------------------
+def _gram(n, q, rng, decades=None):
+    if decades is None:
+        Y = rng.standard_normal((q, n))
+    else:
+        Q1, _ = np.linalg.qr(rng.standard_normal((q, n)))
+        Q2, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        Y = (Q1 * 10.0 ** (-decades * np.arange(n) / n)) @ Q2.T
+    return Y.T @ Y
+
+
+@pytest.mark.parametrize('n,m,decades', [(2, 2, None), (3, 3, None), (12, 6, None), (33, 33, None), (48, 5, None), (200, 100, None),
+                                         (511, 255, None), (512, 256, 3), (512, 256, 6), (512, 512, None)])
+def test_on_chip_eigensolver_matches_lapack(bm, n, m, decades):
+    rng = np.random.default_rng(1000 + n + m)
+    G = _gram(n, max(n, 8), rng, decades)
+    eng = bm.BornEngine(4, 256)
+    lam, U, info = eng.eig_sym(G, m, on_chip=True)
+    lam_ref = np.linalg.eigvalsh(G)
+    lmax = lam_ref[-1]
+    np.testing.assert_allclose(lam, lam_ref, rtol=0, atol=3e-14 * lmax)      # n eps = 1.1e-13 at n = 512
+    assert np.abs(U.T @ U - np.eye(m)).max() < 1e-13
+    assert np.abs(G @ U - U * lam[::-1][:m]).max() < 2e-14 * lmax
+    eng.close()
+
+
+def test_on_chip_eigensolver_structured_matrices(bm):
+    """zero off-diagonals (H_j = I path), decoupled blocks and a low-rank matrix."""
+    rng = np.random.default_rng(77)
+    eng = bm.BornEngine(4, 64)
+    low = rng.standard_normal((48, 5))
+    cases = [(np.diag(np.arange(1.0, 41.0)), 40),
+             (np.kron(np.eye(2), _gram(16, 20, rng)) + np.diag(np.r_[np.zeros(16), np.full(16, 0.37)]), 32),
+             (low @ low.T, 5)]
+    for G, m in cases:
+        lam, U, _ = eng.eig_sym(G, m, on_chip=True)
+        lam_ref = np.linalg.eigvalsh(G)
+        np.testing.assert_allclose(lam, lam_ref, rtol=0, atol=4e-15 * lam_ref[-1])
+        assert np.abs(U.T @ U - np.eye(m)).max() < 1e-13
+        assert np.abs(G @ U - U * lam[::-1][:m]).max() < 2e-14 * lam_ref[-1]
+    eng.close()
+
+
+def test_split_uses_on_chip_eigensolver_and_falls_back(bm):
+    """full-rank bond -> on-chip path; exactly rank-deficient bond (needs deflation levels) -> cuSOLVER fallback;
+    both give the oracle's singular values, and `gram_syevd` never uses the on-chip path."""
+    L, D, N = 10, 6, 80
+    mps, imgs = make_problem(L, D, N, 21, centre=4)
+    phys = o.embed(imgs)
+    cache = o.EnvCache(mps, phys, 'pow2')
+    ref = o.two_site_step(mps, 4, cache.lenv[4], cache.renv[6], phys[:, 4], phys[:, 5], 0.05, True, 'l2', max_bond=8)
+    for svd, expect_fast in (('gram', 1), ('gram_syevd', 0)):
+        eng = engine_for(bm, mps, imgs, cap=8, svd=svd)
+        out = eng.step(4, 0.05, True, 'l2', max_bond=8, want_s=True, advance=False)
+        np.testing.assert_allclose(out['s_all'], ref['s_all'], rtol=1e-9, atol=1e-13)
+        assert eng.eig_stats() == (expect_fast, 0)
+        eng.close()
+    # exact split of a bond with rank < 2D: singular values down to 0 are requested (cutoff 1e-10 keeps 1e-10 s0)
+    mps2, imgs2 = make_problem(8, 2, 40, 31)
+    eng = engine_for(bm, mps2, imgs2, cap=16)
+    eng.step(3, 0.3, True, 'max', max_bond=16, want_s=True)
+    fast, fallback = eng.eig_stats()
+    assert fast + fallback == 1
+    eng.close()
