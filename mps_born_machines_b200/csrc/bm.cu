@@ -78,11 +78,12 @@ struct bm_ctx {
   std::vector<double> h_s;
   int gram_levels = 0;
   // on-chip symmetric eigensolver (bm_eig.cuh): tridiagonal (eD,eE), reflectors (eTau,eV), twisted-factorisation
-  // work arrays eW[4], tridiagonal eigenvectors eZ, 1/norms eZn, polish matrix eC, deviation eDev
+  // tridiagonal eigenvectors eZ, 1/norms eZn, polish matrix eC, deviation eDev
   int eig_ok = 0;            // a 16-CTA cluster can be launched on this device
-  double *eD = nullptr, *eE = nullptr, *eTau = nullptr, *eV = nullptr, *eW = nullptr, *eZ = nullptr, *eZn = nullptr,
-         *eC = nullptr, *eDev = nullptr, *eLam = nullptr;
+  double *eD = nullptr, *eE = nullptr, *eTau = nullptr, *eV = nullptr, *eZ = nullptr, *eZn = nullptr,
+         *eC = nullptr, *eDev = nullptr, *eLam = nullptr, *eGm = nullptr;
   double* h_dev = nullptr;   // pinned
+  int* eig_status = nullptr; // raised by a bounded mbarrier wait of the cluster exchange that timed out
   long long eig_fast = 0, eig_fallback = 0;
   int eig_prof = 0; cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; float eig_ms[5] = {0, 0, 0, 0, 0};
   int* info = nullptr; int* iscal = nullptr;
@@ -211,8 +212,11 @@ int eig_setup(bm_ctx* c) {
   if (cudaOccupancyMaxActiveClusters(&ncl, k_sytrd_cluster, &cfg) != cudaSuccess) { cudaGetLastError(); return BM_OK; }
   if (ncl < 1) return BM_OK;
   const size_t N = EIG_NMAX;
-  DALLOC(c->eD, N); DALLOC(c->eE, N); DALLOC(c->eTau, N); DALLOC(c->eLam, N); DALLOC(c->eZn, N); DALLOC(c->eDev, 2);
-  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eW, 4 * N * N); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N);
+  DALLOC(c->eD, N); DALLOC(c->eE, N); DALLOC(c->eTau, N); DALLOC(c->eLam, N); DALLOC(c->eZn, N); DALLOC(c->eDev, 2); DALLOC(c->eGm, 8 * (N / REFL_CHUNK + 1));
+  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N); DALLOC(c->eig_status, 1);
+  CU(cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->eV, 0, N * EIG_LDV * sizeof(double), c->stream));
+  CU(cudaFuncSetAttribute(k_tri_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM));
   CU(cudaMallocHost((void**)&c->h_dev, 2 * sizeof(double)));
   c->eig_ok = 1;
   return BM_OK;
@@ -221,7 +225,7 @@ int eig_setup(bm_ctx* c) {
 // eigenvalues of the symmetric n x n matrix G (device, ld) -> c->eLam (device, ascending).  Reflectors stay in eV/eTau.
 int eig_values(bm_ctx* c, const double* G, int ld, int n) {
   if (c->eig_prof) cudaEventRecord(c->eig_ev[0], c->stream);
-  k_sytrd_cluster<<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV);
+  k_sytrd_cluster<<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status);
   if (c->eig_prof) cudaEventRecord(c->eig_ev[1], c->stream);
   k_tri_eigvals<<<(n + EIGV_WARPS - 1) / EIGV_WARPS, EIGV_WARPS * 32, 0, c->stream>>>(c->eD, c->eE, n, c->eLam);
   if (c->eig_prof) cudaEventRecord(c->eig_ev[2], c->stream);
@@ -233,10 +237,10 @@ int eig_values(bm_ctx* c, const double* G, int ld, int n) {
 // eigenvectors of the m largest eigenvalues (descending) -> U (n x m, ldu), one Newton-Schulz polish; h_dev[0] =
 // max |U^T U - I| BEFORE the polish (the result deviates by its square).  Synchronises the stream.
 int eig_vectors(bm_ctx* c, int n, int m, double* U, int ldu) {
-  const size_t NN = (size_t)EIG_NMAX * EIG_NMAX;
-  k_tri_vectors<<<(m + 31) / 32, 64, 0, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eW, c->eW + NN, c->eW + 2 * NN, c->eW + 3 * NN, c->eZ, c->eZn);
+  k_tri_vectors<<<(m + TV_EIG - 1) / TV_EIG, 32, TV_SMEM, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eZ, c->eZn);
   if (c->eig_prof) cudaEventRecord(c->eig_ev[3], c->stream);
-  k_apply_reflectors<<<(m + REFL_WARPS - 1) / REFL_WARPS, REFL_WARPS * 32, 0, c->stream>>>(c->eV, c->eTau, n, c->eZ, c->eZn, m, U, ldu);
+  if (n > 2) k_refl_gram<<<(n - 2 + REFL_CHUNK - 1) / REFL_CHUNK, 128, 0, c->stream>>>(c->eV, n, c->eGm);
+  k_apply_reflectors<<<(m + REFL_WARPS - 1) / REFL_WARPS, REFL_WARPS * 32, 0, c->stream>>>(c->eV, c->eTau, c->eGm, n, c->eZ, c->eZn, m, U, ldu);
   if (c->eig_prof) cudaEventRecord(c->eig_ev[4], c->stream);
   c->launches += 2;
   KCHECK();
@@ -444,7 +448,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eW, c->eZ, c->eZn, c->eC, c->eDev, c->eLam, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eDev, c->eLam, c->eGm, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -496,6 +500,9 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
     c->eig_prof = m > 0;
     if (r != BM_OK) return r;
     CU(cudaMemcpyAsync(lam_host, c->eLam, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
     if (m > 0) {
       r = eig_vectors(c, n, m, c->Tmp, n);
       if (r != BM_OK) return r;
@@ -869,7 +876,9 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
     int r = eig_values(c, c->Gq, p, p);
     if (r != BM_OK) return r;
     CU(cudaMemcpyAsync(c->h_lam, c->eLam, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
     const double* lam = c->h_lam;
     const double lmax = lam[p - 1];
     bool ok = lmax > 0.0 && std::isfinite(lmax);

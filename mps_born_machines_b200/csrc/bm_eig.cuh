@@ -48,136 +48,218 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-struct __align__(16) SytrdSmem {
-  double vfull[EIG_NMAX];          // all-gathered Householder vector        (written by every CTA of the cluster)
-  double pfull[EIG_NMAX];          // all-gathered p = tau A v
-  double ppart[EIG_CL][EIG_LR];    // partial A v for my rows, one row per source CTA
-  double scal[EIG_CL][2];          // partial (sum of squares, alpha) per source CTA
-  double dotp[EIG_CL];             // partial p.v per source CTA
-  double vs[EIG_LR], ws[EIG_LR], xs[EIG_LR], ps[EIG_LR];
-};
+// ---- mbarrier + st.async helpers (receiver-side completion: no cluster-wide barrier on the critical path)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(cta));
+  return ra;
+}
+// bulk copy local shared memory -> shared memory of another CTA of the cluster; completes `bytes` of the destination
+// CTA's mbarrier transaction count (ONE mbarrier update per message: per-element st.async updates serialise)
+__device__ __forceinline__ void bulk_copy_to_cta(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 1/x to ~1 ulp without the slow path of a full division (x normal, non-zero)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = r * fma(-0.5 * x * r, r, 1.5);
+  r = r * fma(-0.5 * x * r, r, 1.5);
+  return r;
+}
+// bounded wait (a lost message becomes an error status, never a hang)
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
 
 // G: symmetric n x n (ld), read-only.  Outputs: d[n], e[n-1], tau[n-2], V[j*EIG_LDV + r] = v_j[r] (v_j[j+1] = 1,
 // zeros for r <= j and r >= n).  LAPACK dsytd2 (lower) arithmetic:  H_j = I - tau v v^T,  p = tau A v,
 // w = p - (tau/2)(p.v) v,  A <- A - v w^T - w v^T.
+//
+// Distribution: CTA `me` of the 16-CTA cluster owns rows me, me+16, ... (32 local rows); inside the CTA thread
+// (g, cg) holds the 8x4 register block rows 8g..8g+7 (local) x columns 4cg..4cg+3.  Every CTA also carries the FULL
+// current column j (one element per thread, computed redundantly and bit-identically everywhere), so the Householder
+// vector needs no exchange.  Per column there is ONE exchange: every CTA sends its 32 entries of p, its 32 entries of
+// the not-yet-updated column j+1 and its partial p.v to all CTAs as ONE 528-byte bulk copy per destination
+// (cp.async.bulk shared::cta -> shared::cluster); the receivers wait on a local mbarrier (transaction bytes),
+// double-buffered by the parity of j.
+constexpr int SYTRD_MSG = 2 * EIG_LR + 2;                     // p[32], column slice[32], p.v, pad -> 528 bytes
+constexpr uint32_t SYTRD_TX_BYTES = EIG_CL * SYTRD_MSG * 8;
 __global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_NT, 1)
 k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict__ d, double* __restrict__ e,
-                double* __restrict__ tau, double* __restrict__ V) {
-  __shared__ SytrdSmem sm;
+                double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status) {
+  __shared__ __align__(16) double vfull[EIG_NMAX], wfull[EIG_NMAX];
+  __shared__ __align__(16) double rbuf[2][EIG_CL][SYTRD_MSG];   // received messages, one per source CTA
+  __shared__ __align__(16) double sbuf[2][SYTRD_MSG];           // my outgoing message
+  __shared__ double nrm[EIG_NT / 32];
+  __shared__ double part[EIG_NT / 32][8];
+  __shared__ double cslice[EIG_LR];
+  __shared__ double alpha_sm;
+  __shared__ __align__(8) unsigned long long bars[2];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int me = (int)cluster_ctarank();
-  double a[EIG_LR];
+  const int g = warp >> 2;                        // row group: local rows 8g .. 8g+7
+  const int cg = ((warp & 3) << 5) | lane;        // column group: columns 4cg .. 4cg+3
+  double a[8][4];
 #pragma unroll
-  for (int l = 0; l < EIG_LR; ++l) {
-    const int r = me + EIG_CL * l;
-    a[l] = (t < n && r < n) ? G[(size_t)r * ld + t] : 0.0;     // A[r][t] = G(t, r): coalesced, G is symmetric
+  for (int i = 0; i < 8; ++i) {
+    const int r = me + EIG_CL * (8 * g + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int cidx = 4 * cg + k;
+      a[i][k] = (r < n && cidx < n) ? G[(size_t)r * ld + cidx] : 0.0;     // A[r][c] = G(c, r): G is symmetric
+    }
   }
-  cluster_sync_all();                                          // every CTA is resident before the first remote store
+  double x = t < n ? G[t] : 0.0;                  // full column 0
+  if (t == 0) {
+    mbar_init(eig_smem_u32(&bars[0]), 1);
+    mbar_init(eig_smem_u32(&bars[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                             // every CTA resident, barriers initialised
+  bool ok = true;
   for (int j = 0; j + 2 < n; ++j) {
-    // ---- phase 0: column j on my rows, partial norm
-    if (t == j) {
+    const int par = j & 1;
+    // ---- A: Householder vector from the full column (no exchange)
+    {
+      const double s = warp_sum((t > j + 1) ? x * x : 0.0);
+      if (lane == 0) nrm[warp] = s;
+      if (t == j + 1) alpha_sm = x;
+      if (t == j && me == 0) d[j] = x;
+    }
+    __syncthreads();
+    double xn2 = 0.0;
 #pragma unroll
-      for (int l = 0; l < EIG_LR; ++l) {
-        const int r = me + EIG_CL * l;
-        sm.xs[l] = (r > j) ? a[l] : 0.0;
-        if (r == j) d[j] = a[l];
+    for (int w = 0; w < EIG_NT / 32; ++w) xn2 += nrm[w];
+    const double alpha = alpha_sm;
+    double beta = alpha, tj = 0.0, scale = 0.0;
+    if (xn2 != 0.0) {
+      const double nn = fma(alpha, alpha, xn2);
+      const double rinv = fast_rsqrt(nn);                     // 1/|beta|
+      const double nrm2 = nn * rinv;
+      beta = -copysign(nrm2, alpha);
+      tj = (beta - alpha) * (-copysign(rinv, alpha));          // (beta - alpha) / beta
+      scale = fast_rcp(alpha - beta);
+    }
+    const double vt = (t > j + 1) ? x * scale : (t == j + 1 ? 1.0 : 0.0);
+    vfull[t] = vt;
+    if (cg == ((j + 1) >> 2)) {                   // my 8 entries of the not-yet-updated column j+1
+      const int kk = (j + 1) & 3;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        cslice[8 * g + i] = kk == 0 ? a[i][0] : (kk == 1 ? a[i][1] : (kk == 2 ? a[i][2] : a[i][3]));
+    }
+    __syncthreads();
+    // ---- B: p = tau A v on my rows (reduction over the columns stays inside the CTA)
+    const double2 v01 = *reinterpret_cast<const double2*>(&vfull[4 * cg]);
+    const double2 v23 = *reinterpret_cast<const double2*>(&vfull[4 * cg + 2]);
+    {
+      double q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fma(a[i][0], v01.x, fma(a[i][1], v01.y, fma(a[i][2], v23.x, a[i][3] * v23.y)));
+      // transpose-reduce: 8 row sums over the 32 lanes in 9 shuffles
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double send = (lane & 16) ? q[k] : q[k + 4], keep = (lane & 16) ? q[k + 4] : q[k];
+        q[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
       }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double send = (lane & 8) ? q[k] : q[k + 2], keep = (lane & 8) ? q[k + 2] : q[k];
+        q[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const double send = (lane & 4) ? q[0] : q[1], keep = (lane & 4) ? q[1] : q[0];
+        q[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      q[0] += __shfl_xor_sync(0xffffffffu, q[0], 2);
+      q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+      if ((lane & 3) == 0) part[warp][(((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1)] = q[0];
     }
     __syncthreads();
     if (warp == 0) {
       const int r = me + EIG_CL * lane;
-      const double x = sm.xs[lane];
-      const double ssq = warp_sum((r > j + 1) ? x * x : 0.0);
-      const double al = warp_sum((r == j + 1) ? x : 0.0);
-      if (lane < EIG_CL) {
-        st_cluster_f64(eig_smem_u32(&sm.scal[me][0]), lane, ssq);
-        st_cluster_f64(eig_smem_u32(&sm.scal[me][1]), lane, al);
-      }
+      const int gl = lane >> 3, il = lane & 7;
+      double p = (part[4 * gl][il] + part[4 * gl + 1][il]) + (part[4 * gl + 2][il] + part[4 * gl + 3][il]);
+      p = (r > j && r < n) ? p * tj : 0.0;
+      const double dp = warp_sum(p * vfull[r]);
+      sbuf[par][lane] = p;
+      sbuf[par][EIG_LR + lane] = cslice[lane];
+      if (lane == 0) sbuf[par][2 * EIG_LR] = dp;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(eig_smem_u32(&bars[par]), SYTRD_TX_BYTES);
+      if (lane < EIG_CL)
+        bulk_copy_to_cta(mapa_u32(eig_smem_u32(&rbuf[par][me][0]), lane), eig_smem_u32(&sbuf[par][0]), SYTRD_MSG * 8,
+                         mapa_u32(eig_smem_u32(&bars[par]), lane));
     }
-    cluster_sync_all();                                        // #1
-    double xn2 = 0.0, alpha = 0.0;
-#pragma unroll
-    for (int c = 0; c < EIG_CL; ++c) { xn2 += sm.scal[c][0]; alpha += sm.scal[c][1]; }
-    if (xn2 == 0.0) {                                          // H_j = I (same decision in every CTA: identical inputs)
-      if (me == 0) {
-        V[(size_t)j * EIG_LDV + t] = (t == j + 1) ? 1.0 : 0.0;
-        if (t == 0) { e[j] = alpha; tau[j] = 0.0; }
-      }
-      cluster_sync_all();                                      // nobody rewrites `scal` while a neighbour still reads it
-      continue;
-    }
-    const double beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-    const double tj = (beta - alpha) / beta;
-    const double scale = 1.0 / (alpha - beta);
-    // ---- phase 1: v on my rows -> all-gather; partial A v -> owners of the rows
-    {
-      const int l = t & 31, dst = t >> 5;
-      const int r = me + EIG_CL * l;
-      const double x = sm.xs[l];
-      const double v = (r > j + 1) ? x * scale : (r == j + 1 ? 1.0 : 0.0);
-      st_cluster_f64(eig_smem_u32(&sm.vfull[r]), dst, v);
-      if (dst == 0) sm.vs[l] = v;
-    }
-    __syncthreads();
-    if (t > j && t < n) {
-      double pp = 0.0;
-#pragma unroll
-      for (int l = 0; l < EIG_LR; ++l) pp = fma(a[l], sm.vs[l], pp);
-      st_cluster_f64(eig_smem_u32(&sm.ppart[me][t >> 4]), t & 15, pp);
-    }
-    cluster_sync_all();                                        // #2
-    // ---- phase 2: p on my rows, partial p.v, all-gather p
-    if (warp == 0) {
-      const int r = me + EIG_CL * lane;
-      double p = 0.0;
-      if (r > j && r < n) {
-#pragma unroll
-        for (int s = 0; s < EIG_CL; ++s) p += sm.ppart[s][lane];
-        p *= tj;
-      }
-      sm.ps[lane] = p;
-      const double dp = warp_sum(p * sm.vs[lane]);
-      if (lane < EIG_CL) st_cluster_f64(eig_smem_u32(&sm.dotp[me]), lane, dp);
-    }
-    __syncthreads();
-    {
-      const int l = t & 31, dst = t >> 5;
-      st_cluster_f64(eig_smem_u32(&sm.pfull[me + EIG_CL * l]), dst, sm.ps[l]);
-    }
-    cluster_sync_all();                                        // #3
-    // ---- phase 3: w, rank-2 update of my rows
+    ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
+    // ---- D: w, the next full column, rank-2 update of my block
     double dot = 0.0;
 #pragma unroll
-    for (int c = 0; c < EIG_CL; ++c) dot += sm.dotp[c];
+    for (int c = 0; c < EIG_CL; ++c) dot += rbuf[par][c][2 * EIG_LR];
     const double al2 = -0.5 * tj * dot;
-    const double vt = sm.vfull[t];
-    const double wt = fma(al2, vt, sm.pfull[t]);
-    if (t < EIG_LR) {
-      const int r = me + EIG_CL * t;
-      sm.ws[t] = fma(al2, sm.vfull[r], sm.pfull[r]);
-    }
-    __syncthreads();
-    if (t > j && t < n) {
-      const int l0 = (j + 1 - me + EIG_CL - 1) / EIG_CL;       // first local row with r > j
-#pragma unroll
-      for (int l = 0; l < EIG_LR; ++l)
-        if (l >= l0) a[l] -= fma(sm.vs[l], wt, sm.ws[l] * vt);
-    }
+    const double wt = fma(al2, vt, rbuf[par][t & 15][t >> 4]);
+    const double wj1 = rbuf[par][(j + 1) & 15][(j + 1) >> 4] + al2;   // v[j+1] = 1
+    wfull[t] = wt;
     if (me == (j & (EIG_CL - 1))) {
       V[(size_t)j * EIG_LDV + t] = vt;
       if (t == 0) { e[j] = beta; tau[j] = tj; }
     }
-  }
-  // trailing 2x2 block
+    x = rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);                        // column j+1 of A - v w^T - w v^T
+    __syncthreads();
+    if (4 * cg + 3 > j) {
+      const double2 w01 = *reinterpret_cast<const double2*>(&wfull[4 * cg]);
+      const double2 w23 = *reinterpret_cast<const double2*>(&wfull[4 * cg + 2]);
 #pragma unroll
-  for (int l = 0; l < EIG_LR; ++l) {
-    const int r = me + EIG_CL * l;
-    if (n >= 2 && t == n - 2) {
-      if (r == n - 2) d[n - 2] = a[l];
-      if (r == n - 1) e[n - 2] = a[l];
+      for (int i = 0; i < 8; ++i) {
+        const int r = me + EIG_CL * (8 * g + i);
+        const double vs = vfull[r], ws = wfull[r];
+        a[i][0] -= fma(vs, w01.x, ws * v01.x);
+        a[i][1] -= fma(vs, w01.y, ws * v01.y);
+        a[i][2] -= fma(vs, w23.x, ws * v23.x);
+        a[i][3] -= fma(vs, w23.y, ws * v23.y);
+      }
     }
-    if (t == n - 1 && r == n - 1) d[n - 1] = a[l];
   }
+  // trailing entries: x is the full column n-2 (n >= 2) or column 0 (n == 1)
+  if (me == 0) {
+    if (n >= 2) {
+      if (t == n - 2) d[n - 2] = x;
+      if (t == n - 1) e[n - 2] = x;
+    } else if (t == 0) d[0] = x;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = me + EIG_CL * (8 * g + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (n >= 2 && r == n - 1 && 4 * cg + k == n - 1) d[n - 1] = a[i][k];
+  }
+  if (!ok && t == 0) atomicExch(status, 3);
+  cluster_sync_all();                             // nobody exits while a peer could still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -185,30 +267,60 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
 // Sturm count of eigenvalues < x = sign changes of  p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}  (p_{-1}=0, p_0=1);
 // an exact zero takes the sign opposite to its predecessor.  Both running values are rescaled by a power of two.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int EIGV_WARPS = 8;
-__device__ __forceinline__ int sturm_count(const double* __restrict__ sd, const double* __restrict__ se2, int n, double x) {
-  double pm = 1.0, p = sd[0] - x;
-  bool neg_prev = false;                        // sign of p_0 = 1
-  bool neg = (p < 0.0) || (p == 0.0);           // zero: opposite of the predecessor
-  if (p == 0.0) p = -1e-280;
-  int cnt = neg != neg_prev;
+constexpr int EIGV_WARPS = 4;
+// one recurrence step with the careful zero rule (an exact zero is replaced by a tiny value of the assigned sign,
+// which plays the role of LAPACK's pivmin and restarts the sequence correctly where the matrix splits)
+__device__ __forceinline__ void sturm_step_safe(double dx, double e2, double& p, double& pm, bool& neg_prev, int& cnt) {
+  double pn = fma(dx, p, -e2 * pm);
+  const bool neg = (pn < 0.0) || (pn == 0.0 && !neg_prev);
+  if (pn == 0.0) pn = neg ? -1e-280 : 1e-280;
+  pm = p; p = pn;
+  cnt += neg != neg_prev;
   neg_prev = neg;
-  for (int i = 1; i < n; ++i) {
-    double pn = fma(sd[i] - x, p, -se2[i - 1] * pm);
-    neg = (pn < 0.0) || (pn == 0.0 && !neg_prev);
-    if (pn == 0.0) pn = neg ? -1e-280 : 1e-280; // plays the role of LAPACK's pivmin (|p|,|pm| are kept near 1)
-    pm = p; p = pn;
-    cnt += neg != neg_prev;
-    neg_prev = neg;
-    if ((i & 7) == 7) {                         // exact power-of-two rescaling of the pair
-      const int hi = __double2hiint(fmax(fabs(p), fabs(pm)));
-      const int ex = ((hi >> 20) & 0x7ff) - 1023;
-      if ((ex > 64 || ex < -64) && ex > -900 && ex < 900) {
-        const double s = __hiloint2double((1023 - ex) << 20, 0);
-        p *= s; pm *= s;
-      }
+}
+__device__ __forceinline__ int sturm_count(const double* __restrict__ sd, const double* __restrict__ se2, int n, double x) {
+  double pm = 1.0, p = 0.0;
+  bool neg_prev = false;                        // sign of p_0 = 1
+  int cnt = 0;
+  {                                             // i = 0:  p_1 = (d_0 - x) p_0
+    double p0 = 1.0, pz = 0.0;
+    sturm_step_safe(sd[0] - x, 0.0, p0, pz, neg_prev, cnt);
+    p = p0; pm = 1.0;
+  }
+  int i = 1;
+  for (; i + 8 <= n; i += 8) {
+    double dx[8], e2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { dx[u] = sd[i + u] - x; e2[u] = se2[i + u - 1]; }
+    // speculative fast pass: no zero fix-ups on the dependency chain; sign and zero tests on the integer pipe
+    double fp = p, fpm = pm;
+    int fc = 0, zacc = -1;
+    int fneg = neg_prev ? 1 : 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double pn = fma(dx[u], fp, -e2[u] * fpm);
+      fpm = fp; fp = pn;
+      const int hi = __double2hiint(pn), lo = __double2loint(pn);
+      zacc &= ((hi << 1) | lo) != 0 ? -1 : 0;
+      const int ng = (unsigned)hi >> 31;
+      fc += ng ^ fneg;
+      fneg = ng;
+    }
+    const bool anyzero = zacc == 0;
+    if (!anyzero) { p = fp; pm = fpm; cnt += fc; neg_prev = fneg != 0; }
+    else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sturm_step_safe(dx[u], e2[u], p, pm, neg_prev, cnt);
+    }
+    // exact power-of-two rescaling of the pair (|entries| <= 1 after normalisation: growth <= 3^8 per group)
+    const int hi = __double2hiint(fmax(fabs(p), fabs(pm)));
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    if ((ex > 64 || ex < -64) && ex > -900 && ex < 900) {
+      const double sc = __hiloint2double((1023 - ex) << 20, 0);
+      p *= sc; pm *= sc;
     }
   }
+  for (; i < n; ++i) sturm_step_safe(sd[i] - x, se2[i - 1], p, pm, neg_prev, cnt);
   return cnt;
 }
 
@@ -267,95 +379,130 @@ __global__ void __launch_bounds__(EIGV_WARPS * 32) k_tri_eigvals(const double* _
 // per eigenvalue; work arrays are [i][c] (coalesced over eigenvalues).   Zt[i*m + c] = z_i (unnormalised),
 // znorm[c] = 1/|z|.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_tri_vectors(const double* __restrict__ d, const double* __restrict__ e, int n,
+constexpr int TV_EIG = 8;                                   // eigenvalues per CTA
+constexpr size_t TV_SMEM = (size_t)4 * EIG_NMAX * TV_EIG * sizeof(double) + 2 * EIG_NMAX * sizeof(double);
+__global__ void __launch_bounds__(32) k_tri_vectors(const double* __restrict__ d, const double* __restrict__ e, int n,
                                                     const double* __restrict__ lam, int m,
-                                                    double* __restrict__ wLp, double* __restrict__ wDp,
-                                                    double* __restrict__ wUm, double* __restrict__ wDm,
                                                     double* __restrict__ Zt, double* __restrict__ znorm) {
-  __shared__ double sd[EIG_NMAX], se[EIG_NMAX];
-  __shared__ double gbest[2][32];
-  __shared__ int ibest[2][32];
-  __shared__ double ssq[2][32];
-  const int t = threadIdx.x, lane = t & 31, half = t >> 5;
-  for (int i = t; i < n; i += 64) { sd[i] = d[i]; se[i] = i + 1 < n ? e[i] : 0.0; }
-  __syncthreads();
-  const int c = blockIdx.x * 32 + lane;
-  const bool act = c < m;
+  extern __shared__ __align__(16) double tv_smem[];
+  double* sd = tv_smem;                                    // [n]
+  double* se = sd + EIG_NMAX;                              // [n]
+  double* sDp = se + EIG_NMAX;                             // [n][8]
+  double* sLp = sDp + EIG_NMAX * TV_EIG;
+  double* sDm = sLp + EIG_NMAX * TV_EIG;
+  double* sUm = sDm + EIG_NMAX * TV_EIG;
+  __shared__ double gbest[2][TV_EIG];
+  __shared__ int ibest[2][TV_EIG];
+  __shared__ double ssq[2][TV_EIG];
+  const int lane = threadIdx.x, half = (lane >> 3) & 1, q = lane & 7;
+  for (int i = lane; i < n; i += 32) { sd[i] = d[i]; se[i] = i + 1 < n ? e[i] : 0.0; }
+  __syncwarp();
+  const int c = blockIdx.x * TV_EIG + q;
+  const bool act = lane < 16 && c < m;
   const double x = act ? lam[n - 1 - c] : 0.0;
-  const size_t cs = (size_t)m;
   if (act) {
     if (half == 0) {
       double D = sd[0] - x;
       for (int i = 0; i + 1 < n; ++i) {
         if (D == 0.0) D = DBL_MIN;
-        wDp[i * cs + c] = D;
-        const double Lq = se[i] / D;
-        wLp[i * cs + c] = Lq;
-        D = (sd[i + 1] - x) - Lq * se[i];
+        sDp[i * TV_EIG + q] = D;
+        const double Lq = se[i] * __drcp_rn(D);
+        sLp[i * TV_EIG + q] = Lq;
+        D = fma(-Lq, se[i], sd[i + 1] - x);
       }
-      wDp[(size_t)(n - 1) * cs + c] = D;
+      sDp[(n - 1) * TV_EIG + q] = D;
     } else {
       double D = sd[n - 1] - x;
       for (int i = n - 2; i >= 0; --i) {
         if (D == 0.0) D = DBL_MIN;
-        wDm[(size_t)(i + 1) * cs + c] = D;
-        const double Uq = se[i] / D;
-        wUm[i * cs + c] = Uq;
-        D = (sd[i] - x) - Uq * se[i];
+        sDm[(i + 1) * TV_EIG + q] = D;
+        const double Uq = se[i] * __drcp_rn(D);
+        sUm[i * TV_EIG + q] = Uq;
+        D = fma(-Uq, se[i], sd[i] - x);
       }
-      wDm[c] = D;
+      sDm[q] = D;
     }
   }
-  __syncthreads();
+  __syncwarp();
   const int mid = n / 2;
   if (act) {
     double gb = DBL_MAX; int ib = half == 0 ? 0 : mid;
     const int i0 = half == 0 ? 0 : mid, i1 = half == 0 ? mid : n;
     for (int i = i0; i < i1; ++i) {
-      const double g = fabs(wDp[i * cs + c] + wDm[i * cs + c] - (sd[i] - x));
-      if (g < gb) { gb = g; ib = i; }          // NaN never wins
+      const double gm = fabs(sDp[i * TV_EIG + q] + sDm[i * TV_EIG + q] - (sd[i] - x));
+      if (gm < gb) { gb = gm; ib = i; }          // NaN never wins
     }
-    gbest[half][lane] = gb; ibest[half][lane] = ib;
+    gbest[half][q] = gb; ibest[half][q] = ib;
   }
-  __syncthreads();
-  double s2 = 0.0;
+  __syncwarp();
   if (act) {
-    const int r = (gbest[1][lane] < gbest[0][lane]) ? ibest[1][lane] : ibest[0][lane];
+    const size_t cs = (size_t)m;
+    const int r = (gbest[1][q] < gbest[0][q]) ? ibest[1][q] : ibest[0][q];
+    double s2 = 0.0, z = 1.0;
     if (half == 0) {
-      double z = 1.0;
       Zt[r * cs + c] = 1.0; s2 = 1.0;
       for (int i = r - 1; i >= 0; --i) {
-        z = -wLp[i * cs + c] * z;
+        z = -sLp[i * TV_EIG + q] * z;
         Zt[i * cs + c] = z; s2 = fma(z, z, s2);
       }
     } else {
-      double z = 1.0;
       for (int i = r; i + 1 < n; ++i) {
-        z = -wUm[i * cs + c] * z;
+        z = -sUm[i * TV_EIG + q] * z;
         Zt[(size_t)(i + 1) * cs + c] = z; s2 = fma(z, z, s2);
       }
     }
-    ssq[half][lane] = s2;
+    ssq[half][q] = s2;
   }
-  __syncthreads();
-  if (act && half == 0) znorm[c] = rsqrt(ssq[0][lane] + ssq[1][lane]);
+  __syncwarp();
+  if (act && half == 0) znorm[c] = rsqrt(ssq[0][q] + ssq[1][q]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // back-transformation  U[:, c] = H_0 H_1 ... H_{n-3} z_c / |z_c| : one warp per eigenvector, 16 rows per lane in
 // registers, reflectors streamed from L2 (v_j is zero on rows <= j; row blocks above the support are skipped).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int REFL_WARPS = 8;
-constexpr int REFL_CHUNK = 4;     // reflectors staged per cp.async group
+// Reflectors are applied four at a time (j_a > j_b > j_c > j_d, H_a first).  With the inner products g_xy = v_x.v_y of
+// the four vectors (k_refl_gram, one tiny launch) a single round of warp shuffles serves all four:
+//   f_a = t_a (v_a.z),  f_b = t_b (v_b.z - f_a g_ab),  f_c = t_c (v_c.z - f_a g_ac - f_b g_bc),  f_d = ...,
+//   z <- z - f_a v_a - f_b v_b - f_c v_c - f_d v_d.
+constexpr int REFL_CHUNK = 4;
+constexpr int REFL_WARPS = 4;      // eigenvectors per CTA (one warp each, 16 rows per lane in registers)
+__global__ void __launch_bounds__(128) k_refl_gram(const double* __restrict__ V, int n, double* __restrict__ Gm) {
+  __shared__ double red[4][6];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* vp[REFL_CHUNK];
+#pragma unroll
+  for (int i = 0; i < REFL_CHUNK; ++i) {
+    const int j = n - 3 - (q * REFL_CHUNK + i);
+    vp[i] = j >= 0 ? V + (size_t)j * EIG_LDV : nullptr;
+  }
+  double g[6] = {0, 0, 0, 0, 0, 0};
+  for (int r = tid; r < n; r += 128) {
+    double v[REFL_CHUNK];
+#pragma unroll
+    for (int i = 0; i < REFL_CHUNK; ++i) v[i] = vp[i] ? vp[i][r] : 0.0;
+    g[0] = fma(v[0], v[1], g[0]); g[1] = fma(v[0], v[2], g[1]); g[2] = fma(v[0], v[3], g[2]);
+    g[3] = fma(v[1], v[2], g[3]); g[4] = fma(v[1], v[3], g[4]); g[5] = fma(v[2], v[3], g[5]);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double sgk = warp_sum(g[k]);
+    if (lane == 0) red[warp][k] = sgk;
+  }
+  __syncthreads();
+  if (tid < 6) Gm[(size_t)q * 8 + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+}
+
 __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const double* __restrict__ V, const double* __restrict__ tau,
-                                                                      int n, const double* __restrict__ Zt, const double* __restrict__ znorm,
+                                                                      const double* __restrict__ Gm, int n,
+                                                                      const double* __restrict__ Zt, const double* __restrict__ znorm,
                                                                       int m, double* __restrict__ U, int ldu) {
   __shared__ __align__(16) double sv[2][REFL_CHUNK][EIG_NMAX];
-  __shared__ double stau[2][REFL_CHUNK];
+  __shared__ double ssc[2][16];                                   // tau[4], g[6]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x * REFL_WARPS + warp;
   const bool act = c < m;
-  constexpr int RB = EIG_NMAX / 32;
+  constexpr int RB = EIG_NMAX / 32;                              // 32-row blocks: row = 32 b + lane
   double z[RB];
   const double sc = act ? znorm[c] : 0.0;
   const int nb = (n + 31) / 32;
@@ -366,19 +513,19 @@ __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const doub
   }
   const int steps = n - 2;                                       // j = n-3 ... 0
   const int nchunks = steps > 0 ? (steps + REFL_CHUNK - 1) / REFL_CHUNK : 0;
-  const int npair = nb * 16;                                     // 16-byte pieces per reflector: whole 32-row blocks
-                                                                 // (rows >= n of V hold zeros)
+  const int npair = nb * 16;                                     // 16-byte pieces per reflector (rows >= n of V hold zeros)
   auto issue = [&](int q) {
     const int buf = q & 1;
     for (int idx = tid; idx < REFL_CHUNK * npair; idx += REFL_WARPS * 32) {
       const int i = idx / npair, pc = idx % npair;
       const int j = n - 3 - (q * REFL_CHUNK + i);
       if (j >= 0) cp_async16(&sv[buf][i][pc * 2], V + (size_t)j * EIG_LDV + pc * 2, 16);
+      else { sv[buf][i][pc * 2] = 0.0; sv[buf][i][pc * 2 + 1] = 0.0; }
     }
     if (tid < REFL_CHUNK) {
       const int j = n - 3 - (q * REFL_CHUNK + tid);
-      stau[buf][tid] = j >= 0 ? tau[j] : 0.0;
-    }
+      ssc[buf][tid] = j >= 0 ? tau[j] : 0.0;
+    } else if (tid >= 8 && tid < 14) ssc[buf][tid - 4] = Gm[(size_t)q * 8 + (tid - 8)];
     cp_async_commit();
   };
   if (nchunks > 0) issue(0);
@@ -386,24 +533,33 @@ __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const doub
     if (q + 1 < nchunks) { issue(q + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
     __syncthreads();
     const int buf = q & 1;
+    const int jd = n - 3 - (q * REFL_CHUNK + REFL_CHUNK - 1);     // smallest j of the chunk (may be < 0)
+    const int b0 = (jd > 0 ? jd + 1 : 0) >> 5;                    // first 32-row block touching rows > j_d
+    double va[RB], vb[RB], vc[RB], vd[RB];
+    double da = 0.0, db = 0.0, dc = 0.0, dd = 0.0;
 #pragma unroll
-    for (int i = 0; i < REFL_CHUNK; ++i) {
-      const int j = n - 3 - (q * REFL_CHUNK + i);
-      const double tj = stau[buf][i];
-      if (j < 0 || tj == 0.0) continue;
-      const int b0 = (j + 1) >> 5;                               // first row block that intersects rows > j
-      double v[RB];
-      double dot = 0.0;
-#pragma unroll
-      for (int b = 0; b < RB; ++b) {
-        v[b] = 0.0;
-        if (b >= b0 && b < nb) { v[b] = sv[buf][i][b * 32 + lane]; dot = fma(v[b], z[b], dot); }
+    for (int b = 0; b < RB; ++b) {
+      va[b] = vb[b] = vc[b] = vd[b] = 0.0;
+      if (b >= b0 && b < nb) {
+        va[b] = sv[buf][0][b * 32 + lane]; vb[b] = sv[buf][1][b * 32 + lane];
+        vc[b] = sv[buf][2][b * 32 + lane]; vd[b] = sv[buf][3][b * 32 + lane];
+        da = fma(va[b], z[b], da); db = fma(vb[b], z[b], db);
+        dc = fma(vc[b], z[b], dc); dd = fma(vd[b], z[b], dd);
       }
-      dot = warp_sum(dot) * tj;
-#pragma unroll
-      for (int b = 0; b < RB; ++b)
-        if (b >= b0 && b < nb) z[b] = fma(-dot, v[b], z[b]);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      da += __shfl_xor_sync(0xffffffffu, da, o); db += __shfl_xor_sync(0xffffffffu, db, o);
+      dc += __shfl_xor_sync(0xffffffffu, dc, o); dd += __shfl_xor_sync(0xffffffffu, dd, o);
+    }
+    const double* sq = ssc[buf];
+    const double fa = sq[0] * da;
+    const double fb = sq[1] * (db - fa * sq[4]);
+    const double fc = sq[2] * (dc - fa * sq[5] - fb * sq[7]);
+    const double fd = sq[3] * (dd - fa * sq[6] - fb * sq[8] - fc * sq[9]);
+#pragma unroll
+    for (int b = 0; b < RB; ++b)
+      if (b >= b0 && b < nb) z[b] -= fma(fa, va[b], fma(fb, vb[b], fma(fc, vc[b], fd * vd[b])));
     __syncthreads();
   }
   if (act) {
