@@ -227,8 +227,9 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     l0 = eng.launch_count()
+    eig0 = eng.eig_stats()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    chis = []
+    chis, levels = [], []
     barrier()
     wall0 = time.perf_counter()
     for i in range(steps):
@@ -239,11 +240,13 @@ def run_ours(args):
         out = eng.step(k, 1e-3, True, **kw); k += 1
         ev[i][1].record()
         chis.append(out['chi'])
+        eng.eig_stats(); levels.append(eng.last_gram_levels)
     barrier()
     wall = time.perf_counter() - wall0
     step_ms = [round(a.elapsed_time(b), 3) for a, b in ev]
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = eng.launch_count() - l0
+    eig1 = eng.eig_stats()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=f'cuda:{local}')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -332,7 +335,7 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps,
                     'd2h_bytes_per_step': d2h // steps},
             'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clk,
-            'svd': args.svd, 'allreduce': allreduce_mode, 'chi': int(chis[-1]), 'step_ms': step_ms, 'wall_s_timed': wall, 'setup_s': t_setup,
+            'svd': args.svd, 'split_eig': {'on_chip': eig1[0] - eig0[0], 'cusolver_fallback': eig1[1] - eig0[1]}, 'allreduce': allreduce_mode, 'chi': int(chis[-1]), 'step_ms': step_ms, 'gram_levels': levels, 'wall_s_timed': wall, 'setup_s': t_setup,
             'sweep_s_extrapolated': dev_ms / steps * 1e-3 * 2 * (L - 1),
         }
         if cpu:
@@ -422,7 +425,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS) + ['c4'])
     ap.add_argument('--samples', type=int, default=0)
-    ap.add_argument('--svd', default='gram', choices=['gram', 'gesvdj'])
+    ap.add_argument('--svd', default='gram', choices=['gram', 'gram_syevd', 'gesvdj'])
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-sampler', action='store_true', help='skip the secondary samples/s measurement')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],

@@ -58,8 +58,9 @@ int bm_set_svd(bm_ctx* ctx, int method);
  * U_host (n x m) = eigenvectors of the m largest, descending; info8 = {device ms, max|U^T U - I| before the polish, on_chip,
  * stage ms: tridiagonalisation, eigenvalues, readback+twisted vectors, back-transformation, polish}. */
 int bm_eig_sym(bm_ctx* ctx, int n, const double* G_host, int m, int on_chip, double* lam_host, double* U_host, double* info8);
-/* how many splits ran on the on-chip eigensolver / fell back to cuSOLVER (degenerate or rank-deficient spectra) */
-int bm_eig_stats(bm_ctx* ctx, long long* on_chip, long long* fallback);
+/* how many splits ran on the on-chip eigensolver / fell back to cuSOLVER (degenerate spectra, n > 512), and the
+ * number of deflation levels the last Gram split needed (may be NULL) */
+int bm_eig_stats(bm_ctx* ctx, long long* on_chip, long long* fallback, int* last_levels);
 /* grad_tf32 = 1: accumulate S = sum psi'/psi with tcgen05.mma.kind::tf32 into TMEM (1e-3 parity class; bonds <= 256,
  * larger bonds fall back to the FP64 DMMA kernel).  psi, environments, update and split stay FP64. */
 int bm_set_precision(bm_ctx* ctx, int grad_tf32);

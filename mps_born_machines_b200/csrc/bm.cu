@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -85,6 +86,8 @@ struct bm_ctx {
   double* h_dev = nullptr;   // pinned
   int* eig_status = nullptr; // raised by a bounded mbarrier wait of the cluster exchange that timed out
   long long eig_fast = 0, eig_fallback = 0;
+  int eig_debug = 0;         // BM_EIG_DEBUG=1: per-level stage times of the on-chip split on stderr
+  std::vector<std::pair<const char*, cudaEvent_t>> dbg_ticks;
   int eig_prof = 0; cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; float eig_ms[5] = {0, 0, 0, 0, 0};
   int* info = nullptr; int* iscal = nullptr;
   double *psi = nullptr, *winv = nullptr, *lnpsi = nullptr;
@@ -217,8 +220,11 @@ int eig_setup(bm_ctx* c) {
   CU(cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->eV, 0, N * EIG_LDV * sizeof(double), c->stream));
   CU(cudaFuncSetAttribute(k_tri_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM));
+  CU(cudaFuncSetAttribute(k_apply_reflectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REFL_SMEM));
   CU(cudaMallocHost((void**)&c->h_dev, 2 * sizeof(double)));
   c->eig_ok = 1;
+  if (const char* dbg = std::getenv("BM_EIG_DEBUG")) c->eig_debug = std::atoi(dbg);
+  if (c->eig_debug) for (auto& ev : c->eig_ev) CU(cudaEventCreate(&ev));
   return BM_OK;
 }
 
@@ -234,31 +240,74 @@ int eig_values(bm_ctx* c, const double* G, int ld, int n) {
   return BM_OK;
 }
 
-// eigenvectors of the m largest eigenvalues (descending) -> U (n x m, ldu), one Newton-Schulz polish; h_dev[0] =
-// max |U^T U - I| BEFORE the polish (the result deviates by its square).  Synchronises the stream.
-int eig_vectors(bm_ctx* c, int n, int m, double* U, int ldu) {
-  k_tri_vectors<<<(m + TV_EIG - 1) / TV_EIG, 32, TV_SMEM, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eZ, c->eZn);
-  if (c->eig_prof) cudaEventRecord(c->eig_ev[3], c->stream);
-  if (n > 2) k_refl_gram<<<(n - 2 + REFL_CHUNK - 1) / REFL_CHUNK, 128, 0, c->stream>>>(c->eV, n, c->eGm);
-  k_apply_reflectors<<<(m + REFL_WARPS - 1) / REFL_WARPS, REFL_WARPS * 32, 0, c->stream>>>(c->eV, c->eTau, c->eGm, n, c->eZ, c->eZn, m, U, ldu);
-  if (c->eig_prof) cudaEventRecord(c->eig_ev[4], c->stream);
-  c->launches += 2;
-  KCHECK();
+
+// BM_EIG_DEBUG: named time stamps on the stream, printed (and released) by dbg_flush after a synchronisation
+void dbg_tick(bm_ctx* c, const char* label) {
+  if (!c->eig_debug) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, c->stream);
+  c->dbg_ticks.push_back({label, ev});
+}
+void dbg_flush(bm_ctx* c) {
+  if (!c->eig_debug || c->dbg_ticks.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  std::string line = "[bm eig ticks]";
+  for (size_t i = 1; i < c->dbg_ticks.size(); ++i) {
+    float f = 0.f;
+    cudaEventElapsedTime(&f, c->dbg_ticks[i - 1].second, c->dbg_ticks[i].second);
+    char buf[96];
+    std::snprintf(buf, sizeof buf, " %s %.3f", c->dbg_ticks[i].first, f);
+    line += buf;
+  }
+  for (auto& t : c->dbg_ticks) cudaEventDestroy(t.second);
+  c->dbg_ticks.clear();
+  std::fprintf(stderr, "%s\n", line.c_str());
+}
+
+// cuBLAS picks (and lazily loads, ~10 ms the first time) a kernel per GEMM shape: the column counts of the polish
+// and deflation GEMMs are therefore padded with zero columns to multiples of 64, and those shapes are warmed once.
+inline int pad64(int m, int cap) { return std::min((m + 63) & ~63, cap); }
+
+// Newton-Schulz orthonormality polish of U (n x m, ldu == n, room for `cap` >= m columns):
+// U <- U (1.5 I - 0.5 U^T U), at most two rounds.  h_dev[round] = max |U^T U - I| measured BEFORE that round (the
+// round squares it).  Columns m .. pad64(m) of U are zeroed.  Synchronises the stream.
+int polish_columns(bm_ctx* c, int n, int m, double* U, int ldu, int cap) {
   const double one = 1.0, zero = 0.0;
+  const int mp = ldu == n ? pad64(m, cap) : m;
+  if (mp > m) CU(cudaMemsetAsync(U + (size_t)m * ldu, 0, (size_t)(mp - m) * ldu * sizeof(double), c->stream));
   c->h_dev[0] = c->h_dev[1] = DBL_MAX;
   for (int round = 0; round < 2; ++round) {
-    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, m, m, n, &one, U, ldu, U, ldu, &zero, c->eC, m));
-    k_polish_coef<<<1, 1024, 0, c->stream>>>(c->eC, m, m, c->eDev + round);
+    dbg_tick(c, "[polish");
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mp, mp, n, &one, U, ldu, U, ldu, &zero, c->eC, mp));
+    dbg_tick(c, "UtU");
+    k_polish_coef<<<1, 1024, 0, c->stream>>>(c->eC, mp, mp, m, c->eDev + round);
     c->launches++;
     KCHECK();
-    LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, n, m, m, &one, U, ldu, c->eC, m, &zero, c->eZ, n));
-    CU(cudaMemcpy2DAsync(U, (size_t)ldu * sizeof(double), c->eZ, (size_t)n * sizeof(double), (size_t)n * sizeof(double), m, cudaMemcpyDeviceToDevice, c->stream));
+    dbg_tick(c, "coef");
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, n, mp, mp, &one, U, ldu, c->eC, mp, &zero, c->eZ, n));
+    dbg_tick(c, "UC");
+    CU(cudaMemcpy2DAsync(U, (size_t)ldu * sizeof(double), c->eZ, (size_t)n * sizeof(double), (size_t)n * sizeof(double), mp, cudaMemcpyDeviceToDevice, c->stream));
+    dbg_tick(c, "copy]");
     CU(cudaMemcpyAsync(c->h_dev + round, c->eDev + round, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (round == 0 && c->h_dev[0] < 1e-8) break;      // deviation after the polish ~ square of it: done
     if (round == 0 && !(c->h_dev[0] < 1e-3)) break;   // hopeless (degenerate cluster / NaN): caller falls back
   }
   return BM_OK;
+}
+
+// eigenvectors of the m largest eigenvalues (descending) -> U (n x m, ldu), one Newton-Schulz polish; h_dev[0] =
+// max |U^T U - I| BEFORE the polish (the result deviates by its square).  Synchronises the stream.
+int eig_vectors(bm_ctx* c, int n, int m, double* U, int ldu, int cap) {
+  k_tri_vectors<<<(m + TV_EIG - 1) / TV_EIG, 32, TV_SMEM, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eZ, c->eZn);
+  if (c->eig_prof) cudaEventRecord(c->eig_ev[3], c->stream);
+  if (n > 2) k_refl_gram<<<(n - 2 + REFL_CHUNK - 1) / REFL_CHUNK, 128, 0, c->stream>>>(c->eV, n, c->eGm);
+  k_apply_reflectors<<<(m + REFL_WARPS - 1) / REFL_WARPS, REFL_WARPS * 32, REFL_SMEM, c->stream>>>(c->eV, c->eTau, c->eGm, n, c->eZ, c->eZn, m, U, ldu);
+  if (c->eig_prof) cudaEventRecord(c->eig_ev[4], c->stream);
+  c->launches += 2;
+  KCHECK();
+  return polish_columns(c, n, m, U, ldu, cap);
 }
 
 // persistent panel kernels: one CTA per resident slot, never more CTAs than 16-row work units
@@ -433,6 +482,26 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
   CU(cudaMallocHost((void**)&c->h_lam, (mA + 2) * sizeof(double)));
   r = eig_setup(c);
   if (r != BM_OK) return r;
+  {   // cuSOLVER workspace for the largest Gram matrix up front (a first-use allocation would stall a step by ~10 ms)
+    int lw = 0;
+    LIB(cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)mA, c->Gq, (int)mA, c->lam, &lw));
+    if ((size_t)lw > c->lwork) { DALLOC(c->work, (size_t)lw); c->lwork = (size_t)lw; }
+  }
+  if (c->eig_ok && mA <= EIG_NMAX) {   // load the cuBLAS kernels of the split's GEMM shapes at full bond dimension
+    const int pp = (int)mA;
+    const double one = 1.0, zero = 0.0;
+    CU(cudaMemsetAsync(c->U, 0, mA * mA * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->W, 0, mA * mA * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->Yb[0], 0, mA * mA * sizeof(double), c->stream));
+    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, pp, pp, pp, &one, c->W, pp, c->W, pp, &zero, c->Gq, pp));
+    for (int mp = 64; mp <= pp; mp += 64) {
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mp, mp, pp, &one, c->U, pp, c->U, pp, &zero, c->eC, mp));
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, pp, mp, mp, &one, c->U, pp, c->eC, mp, &zero, c->eZ, pp));
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, pp, mp, pp, &one, c->W, pp, c->U, pp, &zero, c->Tmp, pp));
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_T, pp, pp, mp, &one, c->Tmp, pp, c->U, pp, &one, c->Yb[0], pp));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+  }
   DALLOC(c->partZ, RED_BLOCKS); DALLOC(c->part2, RED_BLOCKS * 4); DALLOC(c->scal, 8);
   CU(cudaMallocHost((void**)&c->h_scal, 8 * sizeof(double)));
   CU(cudaMallocHost((void**)&c->h_iscal, 4 * sizeof(int)));
@@ -504,7 +573,7 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
     CU(cudaStreamSynchronize(c->stream));
     if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
     if (m > 0) {
-      r = eig_vectors(c, n, m, c->Tmp, n);
+      r = eig_vectors(c, n, m, c->Tmp, n, n);
       if (r != BM_OK) return r;
       dev0 = c->h_dev[0];
     }
@@ -541,9 +610,10 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
   return BM_OK;
 }
 
-int bm_eig_stats(bm_ctx* c, long long* on_chip, long long* fallback) {
+int bm_eig_stats(bm_ctx* c, long long* on_chip, long long* fallback, int* last_levels) {
   if (!c || !on_chip || !fallback) return BM_EINVAL;
   *on_chip = c->eig_fast; *fallback = c->eig_fallback;
+  if (last_levels) *last_levels = c->gram_levels;
   return BM_OK;
 }
 
@@ -868,56 +938,107 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
   const double* T = nullptr;
   int pl = p, lev = 0, yb = 0, tb = 0, ncols_out = 0;
   double sigma0sq = 0.0;
-  // ---- fast path: on-chip eigensolver (bm_eig.cuh).  Applies when one Gram level resolves every kept singular value
-  // (all above sqrt(TAU) s_0) and the kept eigenvalues are separated well enough for twisted-factorisation vectors;
-  // otherwise (rank-deficient / degenerate spectra, n > 512) the cuSOLVER levels below run unchanged.
+  // ---- fast path: on-chip eigensolver (bm_eig.cuh), same level structure as the cuSOLVER path below.  A level
+  // resolves the eigenvalues above TAU of its largest; the resolved directions are then projected out of Y
+  // (Y <- Y - (Y U) U^T, on Y so that the small singular values keep their relative accuracy) and the next level runs
+  // on the Gram matrix of the remainder (same size; the projected-out directions reappear as zeros and are skipped).
+  // Falls back to cuSOLVER for n > 512, degenerate eigenvalues among the kept ones, or a failed orthonormality check.
   if (c->svd_method == BM_SVD_GRAM && c->eig_ok && p <= EIG_NMAX && p >= 2) {
-    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, p, p, q, &one, c->W, q, c->W, q, &zero, c->Gq, p));
-    int r = eig_values(c, c->Gq, p, p);
-    if (r != BM_OK) return r;
-    CU(cudaMemcpyAsync(c->h_lam, c->eLam, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
-    const double* lam = c->h_lam;
-    const double lmax = lam[p - 1];
-    bool ok = lmax > 0.0 && std::isfinite(lmax);
-    int kkeep = 0;
-    if (ok) while (kkeep < p && lam[p - 1 - kkeep] > TAU * lmax) ++kkeep;
-    ok = ok && (kkeep >= need || kkeep == p);
-    int chi = 0;
-    if (ok) {
-      sv.resize(p);
-      for (int j = 0; j < p; ++j) sv[j] = std::sqrt(std::max(lam[p - 1 - j], 0.0));
-      if ((int)sv.size() > rmin) sv.resize(rmin);
-      if (cutoff > 0.0) {
-        for (double x : sv) if (x > cutoff * sv[0]) ++chi;
-        chi = std::max(chi, 1);
-        if (max_bond > 0) chi = std::min(chi, max_bond);
-      } else chi = max_bond > 0 ? std::min(max_bond, (int)sv.size()) : (int)sv.size();
-      ok = chi <= kkeep;
-      // separation of the kept eigenvalues (and of the last kept one from the first discarded one)
-      double gap = DBL_MAX;
-      for (int j = 0; j < chi && j + 1 < p; ++j) gap = std::min(gap, lam[p - 1 - j] - lam[p - 2 - j]);
-      ok = ok && (gap > 4.0 * DBL_EPSILON * lmax * 1e5);     // predicted loss of orthogonality below 1e-5
+    const double* Ycur = c->W;
+    bool ok = true, finished = false;
+    int ncols = 0, chi = 0, flev = 0;
+    while (ok && !finished) {
+      ++flev;
+      dbg_tick(c, "[level");
+      LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, p, p, q, &one, Ycur, q, Ycur, q, &zero, c->Gq, p));
+      dbg_tick(c, "gram");
+      c->eig_prof = c->eig_debug;
+      int r = eig_values(c, c->Gq, p, p);
+      if (r != BM_OK) return r;
+      CU(cudaMemcpyAsync(c->h_lam, c->eLam, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
+      const double* lam = c->h_lam;
+      const double lmax = lam[p - 1];
+      const int peff = p - ncols;                              // the ncols smallest are the projected-out directions
+      if (flev == 1) {
+        if (!(lmax > 0.0) || !std::isfinite(lmax)) { ok = false; break; }
+        sigma0sq = lmax;
+      }
+      int kkeep = 0;
+      if (lmax > 0.0) while (kkeep < peff && lam[p - 1 - kkeep] > TAU * lmax) ++kkeep;
+      const int rest = peff - kkeep;
+      const bool done = (ncols + kkeep >= need) || rest == 0 || !(lmax > 0.0) || (TAU * lmax <= cutoff * cutoff * sigma0sq);
+      if (!done && flev >= 8) { ok = false; break; }
+      const int npush = done ? peff : kkeep;
+      for (int j = 0; j < npush; ++j) sv.push_back(std::sqrt(std::max(lam[p - 1 - j], 0.0)));
+      int nv = kkeep;
+      if (done) {
+        if ((int)sv.size() > rmin) sv.resize(rmin);
+        if (cutoff > 0.0) {
+          for (double x : sv) if (x > cutoff * sv[0]) ++chi;
+          chi = std::max(chi, 1);
+          if (max_bond > 0) chi = std::min(chi, max_bond);
+        } else chi = max_bond > 0 ? std::min(max_bond, (int)sv.size()) : (int)sv.size();
+        nv = chi - ncols;
+        if (nv > kkeep) { ok = false; break; }                 // would need vectors of unresolved values
+        if (nv < 0) nv = 0;
+      }
+      if (nv > 0) {
+        // separation of the wanted eigenvalues (and of the last one from its lower neighbour)
+        double gap = DBL_MAX;
+        for (int j = 0; j < nv && j + 1 < p; ++j) gap = std::min(gap, lam[p - 1 - j] - lam[p - 2 - j]);
+        if (!(gap > 4.0 * DBL_EPSILON * lmax * 1e5)) { ok = false; break; }   // predicted loss of orthogonality > 1e-5
+        double* Ulev = iso + (size_t)ncols * p;
+        r = eig_vectors(c, p, nv, Ulev, p, p - ncols);
+        if (r != BM_OK) return r;
+        if (c->eig_debug) {
+          float f[4] = {0, 0, 0, 0};
+          for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&f[i], c->eig_ev[i], c->eig_ev[i + 1]);
+          std::fprintf(stderr, "[bm eig] level %d p=%d ncols=%d kkeep=%d nv=%d done=%d lmax=%.3e | sytrd %.3f eigvals %.3f readback+vectors %.3f reflectors %.3f ms | dev %.2e %.2e\n",
+                       flev, p, ncols, kkeep, nv, (int)done, lmax, f[0], f[1], f[2], f[3], c->h_dev[0], c->h_dev[1]);
+        }
+        c->eig_prof = 0;
+        const double devn = c->h_dev[0] < 1e-8 ? c->h_dev[0] * c->h_dev[0] : c->h_dev[1] * c->h_dev[1];
+        if (!(devn < 1e-13)) { ok = false; break; }
+        if (!done) {                                           // Y <- Y - (Y U) U^T
+          double* Yn = c->Yb[flev & 1];
+          const double mone = -1.0;
+          const int nvp = pad64(nv, p - ncols);                // the padding columns of Ulev are zero (polish_columns)
+          dbg_tick(c, "[deflate");
+          LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, q, nvp, p, &one, Ycur, q, Ulev, p, &zero, c->Tmp, q));
+          dbg_tick(c, "YU");
+          CU(cudaMemcpyAsync(Yn, Ycur, (size_t)q * p * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+          dbg_tick(c, "copy");
+          LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_T, q, p, nvp, &mone, c->Tmp, q, Ulev, p, &one, Yn, q));
+          dbg_tick(c, "Y-TUt]");
+          Ycur = Yn;
+        }
+        ncols += nv;
+      }
+      finished = done;
     }
-    if (ok) {
-      r = eig_vectors(c, p, chi, iso, p);
+    if (ok && flev > 1 && chi > 1) {                           // cross-level orthonormality: one more verified polish
+      int r = polish_columns(c, p, chi, iso, p, p);
       if (r != BM_OK) return r;
       const double devn = c->h_dev[0] < 1e-8 ? c->h_dev[0] * c->h_dev[0] : c->h_dev[1] * c->h_dev[1];
       ok = devn < 1e-13;
     }
     if (ok) {
       c->eig_fast++;
-      c->gram_levels = 1;
+      c->gram_levels = flev;
       double t2 = 0.0;
       for (size_t i = chi; i < sv.size(); ++i) t2 += sv[i] * sv[i];
       *chi_out = chi; *trunc_out = std::sqrt(t2);
       LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, q, chi, p, &one, c->W, q, iso, p, &zero, absb, q));
+      dbg_tick(c, "project");
+      dbg_flush(c);
       return BM_OK;
     }
     c->eig_fallback++;
     sv.clear();
+    sigma0sq = 0.0;
   }
   while (true) {
     ++lev;

@@ -115,7 +115,8 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
   __shared__ double nrm[EIG_NT / 32];
   __shared__ double part[EIG_NT / 32][8];
   __shared__ double cslice[EIG_LR];
-  __shared__ double alpha_sm;
+  __shared__ double scl[4];
+  __shared__ __align__(16) double xfull[EIG_NMAX];
   __shared__ __align__(8) unsigned long long bars[2];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int me = (int)cluster_ctarank();
@@ -142,29 +143,13 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
   bool ok = true;
   for (int j = 0; j + 2 < n; ++j) {
     const int par = j & 1;
-    // ---- A: Householder vector from the full column (no exchange)
+    // ---- A: publish the masked column xh (xh[t] = x[t] for t > j, else 0), partial norms, my part of column j+1
+    xfull[t] = (t > j) ? x : 0.0;
     {
       const double s = warp_sum((t > j + 1) ? x * x : 0.0);
       if (lane == 0) nrm[warp] = s;
-      if (t == j + 1) alpha_sm = x;
       if (t == j && me == 0) d[j] = x;
     }
-    __syncthreads();
-    double xn2 = 0.0;
-#pragma unroll
-    for (int w = 0; w < EIG_NT / 32; ++w) xn2 += nrm[w];
-    const double alpha = alpha_sm;
-    double beta = alpha, tj = 0.0, scale = 0.0;
-    if (xn2 != 0.0) {
-      const double nn = fma(alpha, alpha, xn2);
-      const double rinv = fast_rsqrt(nn);                     // 1/|beta|
-      const double nrm2 = nn * rinv;
-      beta = -copysign(nrm2, alpha);
-      tj = (beta - alpha) * (-copysign(rinv, alpha));          // (beta - alpha) / beta
-      scale = fast_rcp(alpha - beta);
-    }
-    const double vt = (t > j + 1) ? x * scale : (t == j + 1 ? 1.0 : 0.0);
-    vfull[t] = vt;
     if (cg == ((j + 1) >> 2)) {                   // my 8 entries of the not-yet-updated column j+1
       const int kk = (j + 1) & 3;
 #pragma unroll
@@ -172,13 +157,27 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
         cslice[8 * g + i] = kk == 0 ? a[i][0] : (kk == 1 ? a[i][1] : (kk == 2 ? a[i][2] : a[i][3]));
     }
     __syncthreads();
-    // ---- B: p = tau A v on my rows (reduction over the columns stays inside the CTA)
-    const double2 v01 = *reinterpret_cast<const double2*>(&vfull[4 * cg]);
-    const double2 v23 = *reinterpret_cast<const double2*>(&vfull[4 * cg + 2]);
+    // Householder scalars: ONE warp (the others would only repeat them), interleaved with its share of the product
+    if (warp == 0) {
+      const double xn2 = warp_sum(lane < EIG_NT / 32 ? nrm[lane] : 0.0);
+      const double alpha = xfull[j + 1];
+      double beta = alpha, tj = 0.0, scale = 0.0;
+      if (xn2 != 0.0) {
+        const double nn = fma(alpha, alpha, xn2);
+        const double rinv = fast_rsqrt(nn);                     // 1/|beta|
+        beta = -copysign(nn * rinv, alpha);
+        tj = (beta - alpha) * (-copysign(rinv, alpha));          // (beta - alpha) / beta
+        scale = fast_rcp(alpha - beta);
+      }
+      if (lane == 0) { scl[0] = beta; scl[1] = tj; scl[2] = scale; }
+    }
+    // ---- B: q = A xh on my rows (does not need the scalars:  A v = scale (A xh - beta A[:, j+1]))
     {
+      const double2 x01 = *reinterpret_cast<const double2*>(&xfull[4 * cg]);
+      const double2 x23 = *reinterpret_cast<const double2*>(&xfull[4 * cg + 2]);
       double q[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = fma(a[i][0], v01.x, fma(a[i][1], v01.y, fma(a[i][2], v23.x, a[i][3] * v23.y)));
+      for (int i = 0; i < 8; ++i) q[i] = fma(a[i][0], x01.x, fma(a[i][1], x01.y, fma(a[i][2], x23.x, a[i][3] * x23.y)));
       // transpose-reduce: 8 row sums over the 32 lanes in 9 shuffles
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -199,12 +198,14 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       if ((lane & 3) == 0) part[warp][(((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1)] = q[0];
     }
     __syncthreads();
+    const double beta = scl[0], tj = scl[1], scale = scl[2];
     if (warp == 0) {
       const int r = me + EIG_CL * lane;
       const int gl = lane >> 3, il = lane & 7;
-      double p = (part[4 * gl][il] + part[4 * gl + 1][il]) + (part[4 * gl + 2][il] + part[4 * gl + 3][il]);
-      p = (r > j && r < n) ? p * tj : 0.0;
-      const double dp = warp_sum(p * vfull[r]);
+      const double qs = (part[4 * gl][il] + part[4 * gl + 1][il]) + (part[4 * gl + 2][il] + part[4 * gl + 3][il]);
+      const double p = (r > j && r < n) ? (tj * scale) * fma(-beta, cslice[lane], qs) : 0.0;
+      const double vr = (r > j + 1) ? xfull[r] * scale : (r == j + 1 ? 1.0 : 0.0);
+      const double dp = warp_sum(p * vr);
       sbuf[par][lane] = p;
       sbuf[par][EIG_LR + lane] = cslice[lane];
       if (lane == 0) sbuf[par][2 * EIG_LR] = dp;
@@ -215,32 +216,41 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
         bulk_copy_to_cta(mapa_u32(eig_smem_u32(&rbuf[par][me][0]), lane), eig_smem_u32(&sbuf[par][0]), SYTRD_MSG * 8,
                          mapa_u32(eig_smem_u32(&bars[par]), lane));
     }
-    ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
-    // ---- D: w, the next full column, rank-2 update of my block
-    double dot = 0.0;
-#pragma unroll
-    for (int c = 0; c < EIG_CL; ++c) dot += rbuf[par][c][2 * EIG_LR];
-    const double al2 = -0.5 * tj * dot;
-    const double wt = fma(al2, vt, rbuf[par][t & 15][t >> 4]);
-    const double wj1 = rbuf[par][(j + 1) & 15][(j + 1) >> 4] + al2;   // v[j+1] = 1
-    wfull[t] = wt;
+    const double vt = (t > j + 1) ? x * scale : (t == j + 1 ? 1.0 : 0.0);
+    vfull[t] = vt;
     if (me == (j & (EIG_CL - 1))) {
       V[(size_t)j * EIG_LDV + t] = vt;
       if (t == 0) { e[j] = beta; tau[j] = tj; }
     }
-    x = rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);                        // column j+1 of A - v w^T - w v^T
+    ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
+    // ---- D: w, the next full column, rank-2 update of my block
+    double dsum[EIG_CL];
+#pragma unroll
+    for (int c = 0; c < EIG_CL; ++c) dsum[c] = rbuf[par][c][2 * EIG_LR];
+#pragma unroll
+    for (int w = EIG_CL / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int c = 0; c < w; ++c) dsum[c] += dsum[c + w];       // fixed tree: dependent FP64 adds cost ~40 cycles each
+    const double dot = dsum[0];
+    const double al2 = -0.5 * tj * dot;
+    const double wt = fma(al2, vt, rbuf[par][t & 15][t >> 4]);
+    const double wj1 = rbuf[par][(j + 1) & 15][(j + 1) >> 4] + al2;   // v[j+1] = 1
+    wfull[t] = wt;
+    x = rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);      // column j+1 of A - v w^T - w v^T
     __syncthreads();
     if (4 * cg + 3 > j) {
+      const double2 v01 = *reinterpret_cast<const double2*>(&vfull[4 * cg]);
+      const double2 v23 = *reinterpret_cast<const double2*>(&vfull[4 * cg + 2]);
       const double2 w01 = *reinterpret_cast<const double2*>(&wfull[4 * cg]);
       const double2 w23 = *reinterpret_cast<const double2*>(&wfull[4 * cg + 2]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = me + EIG_CL * (8 * g + i);
-        const double vs = vfull[r], ws = wfull[r];
-        a[i][0] -= fma(vs, w01.x, ws * v01.x);
-        a[i][1] -= fma(vs, w01.y, ws * v01.y);
-        a[i][2] -= fma(vs, w23.x, ws * v23.x);
-        a[i][3] -= fma(vs, w23.y, ws * v23.y);
+        const double nvs = -vfull[r], nws = -wfull[r];         // two FMAs per element (the FP64 pipe is the busy one)
+        a[i][0] = fma(nvs, w01.x, fma(nws, v01.x, a[i][0]));
+        a[i][1] = fma(nvs, w01.y, fma(nws, v01.y, a[i][1]));
+        a[i][2] = fma(nvs, w23.x, fma(nws, v23.x, a[i][2]));
+        a[i][3] = fma(nvs, w23.y, fma(nws, v23.y, a[i][3]));
       }
     }
   }
@@ -493,12 +503,15 @@ __global__ void __launch_bounds__(128) k_refl_gram(const double* __restrict__ V,
   if (tid < 6) Gm[(size_t)q * 8 + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
 }
 
+constexpr int REFL_STAGES = 6;     // cp.async ring depth: L2 latency of a 16 KB chunk is ~3x its compute time
+constexpr size_t REFL_SMEM = (size_t)REFL_STAGES * (REFL_CHUNK * EIG_NMAX + 16) * sizeof(double);
 __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const double* __restrict__ V, const double* __restrict__ tau,
                                                                       const double* __restrict__ Gm, int n,
                                                                       const double* __restrict__ Zt, const double* __restrict__ znorm,
                                                                       int m, double* __restrict__ U, int ldu) {
-  __shared__ __align__(16) double sv[2][REFL_CHUNK][EIG_NMAX];
-  __shared__ double ssc[2][16];                                   // tau[4], g[6]
+  extern __shared__ __align__(16) double refl_smem[];
+  double* sv = refl_smem;                                         // [stage][4][512]
+  double* ssc = refl_smem + (size_t)REFL_STAGES * REFL_CHUNK * EIG_NMAX;   // [stage][16]: tau[4], g[6]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x * REFL_WARPS + warp;
   const bool act = c < m;
@@ -515,53 +528,71 @@ __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const doub
   const int nchunks = steps > 0 ? (steps + REFL_CHUNK - 1) / REFL_CHUNK : 0;
   const int npair = nb * 16;                                     // 16-byte pieces per reflector (rows >= n of V hold zeros)
   auto issue = [&](int q) {
-    const int buf = q & 1;
-    for (int idx = tid; idx < REFL_CHUNK * npair; idx += REFL_WARPS * 32) {
-      const int i = idx / npair, pc = idx % npair;
-      const int j = n - 3 - (q * REFL_CHUNK + i);
-      if (j >= 0) cp_async16(&sv[buf][i][pc * 2], V + (size_t)j * EIG_LDV + pc * 2, 16);
-      else { sv[buf][i][pc * 2] = 0.0; sv[buf][i][pc * 2 + 1] = 0.0; }
+    if (q < nchunks) {
+      const int st = q % REFL_STAGES;
+      double* dstv = sv + (size_t)st * REFL_CHUNK * EIG_NMAX;
+#pragma unroll
+      for (int i = 0; i < REFL_CHUNK; ++i) {
+        const int j = n - 3 - (q * REFL_CHUNK + i);
+        const double* src = V + (size_t)(j >= 0 ? j : 0) * EIG_LDV;
+        for (int pc = tid; pc < npair; pc += REFL_WARPS * 32) {
+          if (j >= 0) cp_async16(dstv + i * EIG_NMAX + pc * 2, src + pc * 2, 16);
+          else { dstv[i * EIG_NMAX + pc * 2] = 0.0; dstv[i * EIG_NMAX + pc * 2 + 1] = 0.0; }
+        }
+      }
+      if (tid < REFL_CHUNK) {                                      // scalars ride in the same cp.async group
+        const int j = n - 3 - (q * REFL_CHUNK + tid);
+        if (j >= 0) cp_async8(&ssc[st * 16 + tid], tau + j, 8);
+        else ssc[st * 16 + tid] = 0.0;
+      } else if (tid >= 8 && tid < 14) cp_async8(&ssc[st * 16 + tid - 4], Gm + (size_t)q * 8 + (tid - 8), 8);
     }
-    if (tid < REFL_CHUNK) {
-      const int j = n - 3 - (q * REFL_CHUNK + tid);
-      ssc[buf][tid] = j >= 0 ? tau[j] : 0.0;
-    } else if (tid >= 8 && tid < 14) ssc[buf][tid - 4] = Gm[(size_t)q * 8 + (tid - 8)];
-    cp_async_commit();
+    cp_async_commit();                                            // (possibly empty) group: uniform accounting
   };
-  if (nchunks > 0) issue(0);
+  for (int q = 0; q < REFL_STAGES - 1; ++q) issue(q);
   for (int q = 0; q < nchunks; ++q) {
-    if (q + 1 < nchunks) { issue(q + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-    __syncthreads();
-    const int buf = q & 1;
+    cp_async_wait<REFL_STAGES - 2>();                             // chunk q has landed
+    __syncthreads();                                              // ... for every thread; chunk q-1 is fully consumed
+    issue(q + REFL_STAGES - 1);                                   // refill the stage chunk q-1 occupied
+    const int st = q % REFL_STAGES;
+    const double* cv = sv + (size_t)st * REFL_CHUNK * EIG_NMAX;
     const int jd = n - 3 - (q * REFL_CHUNK + REFL_CHUNK - 1);     // smallest j of the chunk (may be < 0)
     const int b0 = (jd > 0 ? jd + 1 : 0) >> 5;                    // first 32-row block touching rows > j_d
     double va[RB], vb[RB], vc[RB], vd[RB];
-    double da = 0.0, db = 0.0, dc = 0.0, dd = 0.0;
+    // two accumulators per inner product: dependent FP64 FMAs cost ~40 cycles each, the chains must be short
+    double da = 0.0, db = 0.0, dc = 0.0, dd = 0.0, ea = 0.0, eb = 0.0, ec = 0.0, ed = 0.0;
 #pragma unroll
-    for (int b = 0; b < RB; ++b) {
+    for (int b = 0; b < RB; b += 2) {
       va[b] = vb[b] = vc[b] = vd[b] = 0.0;
+      va[b + 1] = vb[b + 1] = vc[b + 1] = vd[b + 1] = 0.0;
       if (b >= b0 && b < nb) {
-        va[b] = sv[buf][0][b * 32 + lane]; vb[b] = sv[buf][1][b * 32 + lane];
-        vc[b] = sv[buf][2][b * 32 + lane]; vd[b] = sv[buf][3][b * 32 + lane];
+        va[b] = cv[b * 32 + lane]; vb[b] = cv[EIG_NMAX + b * 32 + lane];
+        vc[b] = cv[2 * EIG_NMAX + b * 32 + lane]; vd[b] = cv[3 * EIG_NMAX + b * 32 + lane];
         da = fma(va[b], z[b], da); db = fma(vb[b], z[b], db);
         dc = fma(vc[b], z[b], dc); dd = fma(vd[b], z[b], dd);
       }
+      if (b + 1 >= b0 && b + 1 < nb) {
+        va[b + 1] = cv[(b + 1) * 32 + lane]; vb[b + 1] = cv[EIG_NMAX + (b + 1) * 32 + lane];
+        vc[b + 1] = cv[2 * EIG_NMAX + (b + 1) * 32 + lane]; vd[b + 1] = cv[3 * EIG_NMAX + (b + 1) * 32 + lane];
+        ea = fma(va[b + 1], z[b + 1], ea); eb = fma(vb[b + 1], z[b + 1], eb);
+        ec = fma(vc[b + 1], z[b + 1], ec); ed = fma(vd[b + 1], z[b + 1], ed);
+      }
     }
+    da += ea; db += eb; dc += ec; dd += ed;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       da += __shfl_xor_sync(0xffffffffu, da, o); db += __shfl_xor_sync(0xffffffffu, db, o);
       dc += __shfl_xor_sync(0xffffffffu, dc, o); dd += __shfl_xor_sync(0xffffffffu, dd, o);
     }
-    const double* sq = ssc[buf];
-    const double fa = sq[0] * da;
-    const double fb = sq[1] * (db - fa * sq[4]);
-    const double fc = sq[2] * (dc - fa * sq[5] - fb * sq[7]);
-    const double fd = sq[3] * (dd - fa * sq[6] - fb * sq[8] - fc * sq[9]);
+    const double* sq = ssc + st * 16;
+    const double fa = -sq[0] * da;                                // negated coefficients: z += f_a v_a + ...
+    const double fb = -sq[1] * fma(fa, sq[4], db);
+    const double fc = -sq[2] * fma(fb, sq[7], fma(fa, sq[5], dc));
+    const double fd = -sq[3] * fma(fc, sq[9], fma(fb, sq[8], fma(fa, sq[6], dd)));
 #pragma unroll
     for (int b = 0; b < RB; ++b)
-      if (b >= b0 && b < nb) z[b] -= fma(fa, va[b], fma(fb, vb[b], fma(fc, vc[b], fd * vd[b])));
-    __syncthreads();
+      if (b >= b0 && b < nb) z[b] = fma(fa, va[b], fma(fb, vb[b], fma(fc, vc[b], fma(fd, vd[b], z[b]))));
   }
+  cp_async_wait<0>();
   if (act) {
 #pragma unroll
     for (int b = 0; b < RB; ++b) {
@@ -571,17 +602,20 @@ __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const doub
   }
 }
 
-// C (m x m, ld) holds U^T U.  dev[0] = max |C - I| (must be zeroed by the caller: one CTA, no atomics needed);
-// C <- 1.5 I - 0.5 C, the Newton-Schulz factor:  U <- U C  squares the deviation from orthonormality.
-__global__ void __launch_bounds__(1024) k_polish_coef(double* __restrict__ C, int m, int ld, double* __restrict__ dev) {
+// C (mp x mp, ld) holds U^T U, of which the leading m x m block belongs to real columns (the rest is zero padding that
+// keeps the cuBLAS shapes on multiples of 64).  dev[0] = max |C - I| over the real block; C <- 1.5 I - 0.5 C, the
+// Newton-Schulz factor:  U <- U C  squares the deviation from orthonormality (zero columns stay zero).
+__global__ void __launch_bounds__(1024) k_polish_coef(double* __restrict__ C, int mp, int ld, int m, double* __restrict__ dev) {
   __shared__ double red[32];
   double mx = 0.0;
-  const int total = m * m;
+  const int total = mp * mp;
   for (int idx = threadIdx.x; idx < total; idx += 1024) {
-    const int j = idx / m, i = idx % m;
+    const int j = idx / mp, i = idx % mp;
     const double x = C[(size_t)j * ld + i];
-    const double dv = fabs(x - (i == j ? 1.0 : 0.0));
-    if (!(dv <= mx)) mx = (dv == dv) ? dv : DBL_MAX;      // NaN -> reported as a huge deviation
+    if (i < m && j < m) {
+      const double dv = fabs(x - (i == j ? 1.0 : 0.0));
+      if (!(dv <= mx)) mx = (dv == dv) ? dv : DBL_MAX;      // NaN -> reported as a huge deviation
+    }
     C[(size_t)j * ld + i] = (i == j ? 1.5 : 0.0) - 0.5 * x;
   }
 #pragma unroll

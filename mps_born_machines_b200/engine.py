@@ -391,8 +391,9 @@ class BornEngine:
 
     def eig_stats(self):
         """(splits that ran on the on-chip eigensolver, splits that fell back to cuSOLVER syevd)"""
-        a, b = C.c_longlong(), C.c_longlong()
-        check(self._ctx, self._lib.bm_eig_stats(self._ctx, C.byref(a), C.byref(b)))
+        a, b, lv = C.c_longlong(), C.c_longlong(), C.c_int()
+        check(self._ctx, self._lib.bm_eig_stats(self._ctx, C.byref(a), C.byref(b), C.byref(lv)))
+        self.last_gram_levels = lv.value
         return a.value, b.value
 
 
