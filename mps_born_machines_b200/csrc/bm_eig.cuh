@@ -172,7 +172,12 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       if (lane == 0) { scl[0] = beta; scl[1] = tj; scl[2] = scale; }
     }
     // ---- B: q = A xh on my rows (does not need the scalars:  A v = scale (A xh - beta A[:, j+1]))
-    {
+    // A warp's 64 x 128 tile is dead once all its columns or all its rows are <= j (the trailing block shrinks):
+    // dead tiles contribute zeros and are skipped, in the product and in the update (a third of the work on average).
+    const bool live = (128 * (warp & 3) + 127 > j) && (me + EIG_CL * (8 * g + 7) > j);
+    if (!live) {
+      if ((lane & 3) == 0) part[warp][lane >> 2] = 0.0;
+    } else {
       const double2 x01 = *reinterpret_cast<const double2*>(&xfull[4 * cg]);
       const double2 x23 = *reinterpret_cast<const double2*>(&xfull[4 * cg + 2]);
       double q[8];
@@ -238,7 +243,7 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
     wfull[t] = wt;
     x = rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);      // column j+1 of A - v w^T - w v^T
     __syncthreads();
-    if (4 * cg + 3 > j) {
+    if (live && 4 * cg + 3 > j) {
       const double2 v01 = *reinterpret_cast<const double2*>(&vfull[4 * cg]);
       const double2 v23 = *reinterpret_cast<const double2*>(&vfull[4 * cg + 2]);
       const double2 w01 = *reinterpret_cast<const double2*>(&wfull[4 * cg]);
@@ -246,6 +251,7 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = me + EIG_CL * (8 * g + i);
+        if (r <= j) continue;                                  // warp-uniform: finished rows of a partly live tile
         const double nvs = -vfull[r], nws = -wfull[r];         // two FMAs per element (the FP64 pipe is the busy one)
         a[i][0] = fma(nvs, w01.x, fma(nws, v01.x, a[i][0]));
         a[i][1] = fma(nvs, w01.y, fma(nws, v01.y, a[i][1]));
