@@ -50,22 +50,40 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+    The timed region of the headline workload is only ~60 ms, shorter than nvidia-smi's start-up, so the sampler is
+    started (and known to be printing) BEFORE the warm-up steps; `mark()` brackets the timed region and `stop()`
+    reports the samples whose timestamps fall inside it (falling back to everything since the start, with a note)."""
+    Q = 'timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, gpu_index=0):
         self.path = tempfile.mktemp(suffix='.csv')
         self.proc = None
         self.gpu = gpu_index
+        self.t0 = self.t1 = None
 
-    def start(self):
+    def start(self, wait_s=3.0):
         try:
             self.f = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.gpu), '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          '-i', str(self.gpu), '-lms', '10'], stdout=self.f, stderr=subprocess.DEVNULL)
+            t_end = time.time() + wait_s
+            while time.time() < t_end and os.path.getsize(self.path) == 0:     # first sample printed: sampler is live
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        if self.t0 is None:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
+
+    @staticmethod
+    def _ts(text):
+        import datetime
+        return datetime.datetime.strptime(text.strip(), '%Y/%m/%d %H:%M:%S.%f').timestamp()
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
@@ -77,25 +95,32 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(',')]
                 if len(p) < 9:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
+                    ts = self._ts(p[0])
+                except Exception:
+                    ts = None
+                try:
+                    rows.append((ts, float(p[1]), float(p[2]),
+                                 [name for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9])
+                                  if v.lower().startswith('active')]))
                 except ValueError:
                     continue
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out['sm_mhz'] = float(np.median(sm)); out['sm_max_mhz'] = float(np.max(mx)); out['reasons'] = sorted(reasons)
-            out['samples'] = len(sm)
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None
+                  and self.t0 - 0.015 <= r[0] <= self.t1 + 0.015]
+        use, window = (inside, 'timed region') if inside else (rows, 'warm-up + timed region (no sample fell inside the timed region)')
+        if use:
+            out['sm_mhz'] = float(np.median([r[1] for r in use])); out['sm_max_mhz'] = float(np.max([r[2] for r in use]))
+            out['reasons'] = sorted({x for r in use for x in r[3]})
+            out['samples'] = len(use); out['window'] = window
         return out
 
 
@@ -219,18 +244,19 @@ def run_ours(args):
 
     kw = dict(renorm='l2', max_bond=D, cutoff=1e-10)
     k = start
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                    # live before the warm-up: the timed region is shorter than its start-up
     for _ in range(warm):
         eng.step(k, 1e-3, True, **kw); k += 1
 
     # ---- timed: EXACTLY `steps` steps, device-resident inputs
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     l0 = eng.launch_count()
     eig0 = eng.eig_stats()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     chis, levels = [], []
     barrier()
+    clocks.mark()
     wall0 = time.perf_counter()
     for i in range(steps):
         if flush is not None:
@@ -243,6 +269,7 @@ def run_ours(args):
         eng.eig_stats(); levels.append(eng.last_gram_levels)
     barrier()
     wall = time.perf_counter() - wall0
+    clocks.mark()
     step_ms = [round(a.elapsed_time(b), 3) for a, b in ev]
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = eng.launch_count() - l0
@@ -370,7 +397,9 @@ def run_sampler(args):
     if rank == 0:
         clocks.start()
     l0 = eng.launch_count()
+    clocks.mark()
     ms = [eng.sample_device_ms(n_loc, seed=100 + i) for i in range(args.steps)]
+    clocks.mark()
     launches = eng.launch_count() - l0
     clk = clocks.stop() if rank == 0 else {}
     t = torch.tensor([sum(ms)], dtype=torch.float64, device=f'cuda:{local}')
