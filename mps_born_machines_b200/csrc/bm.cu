@@ -281,7 +281,8 @@ int polish_columns(bm_ctx* c, int n, int m, double* U, int ldu, int cap) {
     dbg_tick(c, "[polish");
     LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mp, mp, n, &one, U, ldu, U, ldu, &zero, c->eC, mp));
     dbg_tick(c, "UtU");
-    k_polish_coef<<<1, 1024, 0, c->stream>>>(c->eC, mp, mp, m, c->eDev + round);
+    CU(cudaMemsetAsync(c->eDev + round, 0, sizeof(double), c->stream));
+    k_polish_coef<<<POLISH_BLOCKS, 256, 0, c->stream>>>(c->eC, mp, mp, m, c->eDev + round);
     c->launches++;
     KCHECK();
     dbg_tick(c, "coef");
@@ -962,8 +963,11 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
       const double* lam = c->h_lam;
       const double lmax = lam[p - 1];
       const int peff = p - ncols;                              // the ncols smallest are the projected-out directions
+      bool finite = true;
+      for (int j = 0; j < p; ++j) finite = finite && std::isfinite(lam[j]);
+      if (!finite) { ok = false; break; }                      // e.g. denormal trailing columns: let LAPACK-style code decide
       if (flev == 1) {
-        if (!(lmax > 0.0) || !std::isfinite(lmax)) { ok = false; break; }
+        if (!(lmax > 0.0)) { ok = false; break; }
         sigma0sq = lmax;
       }
       int kkeep = 0;

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(EIGV_WARPS * 32) k_tri_eigvals(const double* _
 // eigenvectors of the m LARGEST eigenvalues (vector c belongs to lam[n-1-c]) by twisted factorisation:
 // T - x I = L+ D+ L+^T from the top, U- D- U-^T from the bottom, gamma_i = D+_i + D-_i - (d_i - x); with r = argmin
 // |gamma|:  z_r = 1,  z_i = -L+_i z_{i+1} (i < r),  z_{i+1} = -U-_i z_i (i >= r).   Thread pair (forward, backward)
-// per eigenvalue; work arrays are [i][c] (coalesced over eigenvalues).   Zt[i*m + c] = z_i (unnormalised),
+// per eigenvalue, 8 eigenvalues per CTA, the four factor arrays [i][8] in shared memory.   Zt[i*m + c] = z_i (unnormalised),
 // znorm[c] = 1/|z|.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TV_EIG = 8;                                   // eigenvalues per CTA
@@ -617,28 +617,33 @@ __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const doub
 }
 
 // C (mp x mp, ld) holds U^T U, of which the leading m x m block belongs to real columns (the rest is zero padding that
-// keeps the cuBLAS shapes on multiples of 64).  dev[0] = max |C - I| over the real block; C <- 1.5 I - 0.5 C, the
+// keeps the cuBLAS shapes on multiples of 64).  dev[0] = max(dev[0], max |C - I| over the real block) -- zero it
+// before the launch; C <- 1.5 I - 0.5 C, the
 // Newton-Schulz factor:  U <- U C  squares the deviation from orthonormality (zero columns stay zero).
-__global__ void __launch_bounds__(1024) k_polish_coef(double* __restrict__ C, int mp, int ld, int m, double* __restrict__ dev) {
-  __shared__ double red[32];
+constexpr int POLISH_BLOCKS = 64;
+__global__ void __launch_bounds__(256) k_polish_coef(double* __restrict__ C, int mp, int ld, int m, double* __restrict__ dev) {
+  __shared__ double red[8];
   double mx = 0.0;
-  const int total = mp * mp;
-  for (int idx = threadIdx.x; idx < total; idx += 1024) {
-    const int j = idx / mp, i = idx % mp;
-    const double x = C[(size_t)j * ld + i];
-    if (i < m && j < m) {
-      const double dv = fabs(x - (i == j ? 1.0 : 0.0));
-      if (!(dv <= mx)) mx = (dv == dv) ? dv : DBL_MAX;      // NaN -> reported as a huge deviation
+  // one column per step of the block loop: no integer division
+  for (int j = blockIdx.x; j < mp; j += gridDim.x) {
+    double* col = C + (size_t)j * ld;
+    for (int i = threadIdx.x; i < mp; i += 256) {
+      const double x = col[i];
+      if (i < m && j < m) {
+        const double dv = fabs(x - (i == j ? 1.0 : 0.0));
+        if (!(dv <= mx)) mx = (dv == dv) ? dv : DBL_MAX;    // NaN -> reported as a huge deviation
+      }
+      col[i] = (i == j ? 1.5 : 0.0) - 0.5 * x;
     }
-    C[(size_t)j * ld + i] = (i == j ? 1.5 : 0.0) - 0.5 * x;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 0; w < 32; ++w) mx = fmax(mx, red[w]);
-    dev[0] = mx;
+    for (int w = 0; w < 8; ++w) mx = fmax(mx, red[w]);
+    // non-negative doubles order like their bit patterns: max over the CTAs with an integer atomic (dev zeroed by the caller)
+    atomicMax(reinterpret_cast<unsigned long long*>(dev), (unsigned long long)__double_as_longlong(mx));
   }
 }
 

@@ -1274,7 +1274,20 @@ __global__ void __launch_bounds__(1024) k_lnpsi_reduce(const double* __restrict_
   __shared__ double sh[32];
   double s = 0.0, z = 0.0;
   // fixed assignment of elements to threads + fixed-order tree => deterministic
-  for (int i = threadIdx.x; i < m; i += 1024) {
+  // four independent gathers in flight per thread (the loads are dependent: ids -> psi, lnpsi); the additions keep
+  // their order, so the result is unchanged
+  int i = threadIdx.x;
+  for (; i + 3 * 1024 < m; i += 4 * 1024) {
+    int id[4];
+    double ps[4], ln[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) id[u] = ids ? ids[i + u * 1024] : i + u * 1024;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { ps[u] = psi[id[u]]; ln[u] = lnpsi[id[u]]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { if (ps[u] == 0.0) z += 1.0; else s += ln[u]; }
+  }
+  for (; i < m; i += 1024) {
     int id = ids ? ids[i] : i;
     if (psi[id] == 0.0) z += 1.0; else s += lnpsi[id];
   }
