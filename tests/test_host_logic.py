@@ -181,3 +181,15 @@ def test_facade_save_load_and_meanpool(tmp_path, monkeypatch):
         want.append([np.mean([a[c, r], a[c, r + 1], a[c + 1, r], a[c + 1, r + 1]]) for c in range(0, 4, 2) for r in range(0, 4, 2)])
     want = (np.array(want) > 0.3).astype(float)
     assert np.array_equal(T.meanpool2d(imgs, (4, 4)), want)
+
+
+def test_enum_values_match_header():
+    """the Python-side option tables carry the numeric values include/bm.h defines"""
+    import re
+    from mps_born_machines_b200 import _capi
+    hdr = open(os.path.join(os.path.dirname(__file__), '..', 'include', 'bm.h')).read()
+    vals = {k: int(v) for k, v in re.findall(r'\b(BM_[A-Z0-9_]+)\s*=\s*(\d+)', hdr)}
+    assert _capi.SVD == {'gesvdj': vals['BM_SVD_GESVDJ'], 'gesvd': vals['BM_SVD_GESVD'], 'gram': vals['BM_SVD_GRAM'],
+                         'gram_syevd': vals['BM_SVD_GRAM_SYEVD']}
+    assert _capi.RENORM == {'max': vals['BM_RENORM_MAX'], 'l2': vals['BM_RENORM_L2']}
+    assert _capi.RULE == {'batched': vals['BM_RULE_BATCHED'], 'single': vals['BM_RULE_SINGLE']}
