@@ -199,6 +199,7 @@ int set_func_attrs(bm_ctx* c) {
 
 
 // ---- on-chip symmetric eigensolver (bm_eig.cuh) -----------------------------------------------------------------
+constexpr int BM_EIG_UNAVAILABLE = -1;   // internal: cluster launch refused, use cuSOLVER
 int eig_setup(bm_ctx* c) {
   c->eig_ok = 0;
   if (cudaFuncSetAttribute(k_sytrd_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
@@ -232,6 +233,11 @@ int eig_setup(bm_ctx* c) {
 int eig_values(bm_ctx* c, const double* G, int ld, int n) {
   if (c->eig_prof) cudaEventRecord(c->eig_ev[0], c->stream);
   k_sytrd_cluster<<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status);
+  if (cudaPeekAtLastError() != cudaSuccess) {      // the cluster cannot be placed after all (e.g. a partitioned GPU):
+    cudaGetLastError();                            // stop using the on-chip path, the caller falls back to cuSOLVER
+    c->eig_ok = 0;
+    return BM_EIG_UNAVAILABLE;
+  }
   if (c->eig_prof) cudaEventRecord(c->eig_ev[1], c->stream);
   k_tri_eigvals<<<(n + EIGV_WARPS - 1) / EIGV_WARPS, EIGV_WARPS * 32, 0, c->stream>>>(c->eD, c->eE, n, c->eLam);
   if (c->eig_prof) cudaEventRecord(c->eig_ev[2], c->stream);
@@ -568,6 +574,7 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
     c->eig_prof = 1;
     int r = eig_values(c, c->Gq, n, n);
     c->eig_prof = m > 0;
+    if (r == BM_EIG_UNAVAILABLE) return fail(c, BM_ECUDA, "bm_eig_sym: the 16-CTA cluster could not be launched on this device");
     if (r != BM_OK) return r;
     CU(cudaMemcpyAsync(lam_host, c->eLam, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -955,6 +962,7 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
       dbg_tick(c, "gram");
       c->eig_prof = c->eig_debug;
       int r = eig_values(c, c->Gq, p, p);
+      if (r == BM_EIG_UNAVAILABLE) { ok = false; break; }
       if (r != BM_OK) return r;
       CU(cudaMemcpyAsync(c->h_lam, c->eLam, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
