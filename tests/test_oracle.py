@@ -239,3 +239,26 @@ def test_cached_path_matches_reference(golden_dir):
     assert lr == float(f['epoch_lr']) and o.bond_sizes(m2) == list(f['epoch_bonds'])
     trained = [f[f'trained{k}'] for k in range(L)]
     assert np.array_equal(o.generate_samples(trained, f['uniforms']), f['samples'])
+
+
+def test_eigensolver_algorithm_prototype():
+    """numpy restatement of the split's on-chip eigensolver (tools/eigfast_proto.py: Householder tridiagonalisation,
+    multisection with Sturm counts, twisted-factorisation vectors, back-transformation, Newton-Schulz polish) against
+    LAPACK — the algorithm the CUDA kernels of csrc/bm_eig.cuh implement, checked without a GPU."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(__file__), '..', 'tools', 'eigfast_proto.py')
+    spec = importlib.util.spec_from_file_location('eigfast_proto', path)
+    proto = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(proto)
+    rng = np.random.default_rng(5)
+    n, m = 40, 20
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    s = 10.0 ** (-4 * np.arange(n) / n)
+    G = (Q * s ** 2) @ Q.T
+    lam, U = proto.eig_fast(G, m)
+    lam_ref = np.linalg.eigvalsh(G)
+    np.testing.assert_allclose(lam, lam_ref, rtol=0, atol=1e-14 * lam_ref[-1])
+    assert np.abs(U.T @ U - np.eye(m)).max() < 1e-9            # before the polish: eps * |T| / gap
+    U = proto.polish(U, 1)
+    assert np.abs(U.T @ U - np.eye(m)).max() < 1e-14
+    assert np.abs(G @ U - U * lam[::-1][:m]).max() < 1e-14 * lam_ref[-1]
