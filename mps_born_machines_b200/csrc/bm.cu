@@ -533,6 +533,8 @@ int bm_destroy(bm_ctx* c) {
   if (c->h_iscal) cudaFreeHost(c->h_iscal);
   if (c->h_lam) cudaFreeHost(c->h_lam);
   if (c->h_dev) cudaFreeHost(c->h_dev);
+  for (auto& ev : c->eig_ev) if (ev) cudaEventDestroy(ev);
+  for (auto& tk : c->dbg_ticks) cudaEventDestroy(tk.second);
   if (c->tev[0]) { cudaEventDestroy(c->tev[0]); cudaEventDestroy(c->tev[1]); }
   if (c->gesvdj) cusolverDnDestroyGesvdjInfo(c->gesvdj);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
