@@ -1,12 +1,18 @@
 """Build libbm.so in-tree with nvcc for sm_100a (no JIT cache, the .so travels with the repo snapshot)."""
+import glob
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'bm.cu')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'bm_kernels.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'bm.h')]
 OUT = os.path.join(HERE, '_lib', 'libbm.so')
+
+
+def _deps():
+    # every source the library is built from: a stale .so after an edit to ANY header would silently run old kernels
+    return sorted(glob.glob(os.path.join(HERE, 'csrc', '*.cu*')) + glob.glob(os.path.join(os.path.dirname(HERE), 'include', '*.h')))
+
 
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17', '-lcublas', '-lcusolver']
@@ -16,7 +22,7 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(p) > t for p in DEPS)
+    return any(os.path.getmtime(p) > t for p in _deps())
 
 
 def build(force=False, verbose=False, defines=(), out=None):
