@@ -104,11 +104,21 @@ int bm_step_grad(bm_ctx* ctx, int k, const int32_t* mask_host, int n_mask, doubl
  * A <- A - lr*(dNLL + mom_bias), renormalise, thin SVD of the (Dl*d)x(Dr*d) matricisation, keep
  * s_i > cutoff*s_0 (>=1), cap at max_bond (<=0: none), absorb s right (going_right) or left, write the
  * two new site tensors.  scalars_host[8] out: Z, sum ln|psi|, n_zero_psi, chi, mean(dNLL), renorm
- * divisor, truncation error sqrt(sum discarded s^2), 0.  Returns BM_EZERO_PSI without updating when a
- * psi is zero.  s_host (optional) receives all min(rows,cols) singular values. */
+ * divisor, truncation error sqrt(sum discarded s^2), 0.  When a psi is zero (n_zero_psi > 0) the descent is
+ * skipped on the device (lr = 0) but the tensor is still renormalised and split, as the reference does
+ * (TNutils.py:1244-1254).  s_host (optional) receives all min(rows,cols) singular values. */
 int bm_step_update(bm_ctx* ctx, int k, const double* S_dev, double batch_total, double lr, int renorm,
                    int going_right, int max_bond, double cutoff, double mom_bias,
                    double* scalars_host, double* s_host);
+
+/* One whole two-site step in one call: learning_step_cached + write-back + sequential_update
+ * (TNutils.py:1603-1620) = bm_step_grad + bm_step_update (+ bm_env_advance when advance != 0) without
+ * returning to the caller in between; the host synchronises once per Gram level (eigenvalues) and once at
+ * the end.  S_dev: scratch of rows*ld + 2 doubles (bm_grad_dims).  With several ranks this entry needs the
+ * fused peer all-reduce (bm_peer_import); the NCCL path goes through bm_step_grad / bm_step_update. */
+int bm_step(bm_ctx* ctx, int k, const int32_t* mask_host, int n_mask, double* S_dev, double batch_total,
+            double lr, int renorm, int going_right, int max_bond, double cutoff, double mom_bias, int advance,
+            double* scalars_host, double* s_host);
 
 /* Merge + split of bond k without a gradient step or renormalisation: the primitive of `compress`,
  * `compress_copy`, `compress2` (TNutils.py:930-993) and of SVD-based canonicalisation sweeps. */

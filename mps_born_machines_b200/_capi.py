@@ -33,6 +33,8 @@ _SIGS = [
     ('bm_step_grad', C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     ('bm_step_update', C.c_int, [_P, C.c_int, _P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
                                  C.c_double, _P, _P]),
+    ('bm_step', C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
+                          C.c_double, C.c_int, _P, _P]),
     ('bm_split_bond', C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]),
     ('bm_get_merged', C.c_int, [_P, _P]),
     ('bm_ref_to_engine', C.c_int, [_P, C.c_int, _P, _P]),

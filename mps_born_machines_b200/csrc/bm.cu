@@ -15,6 +15,7 @@
 #include "../../include/bm.h"
 #include "bm_kernels.cuh"
 #include "bm_eig.cuh"
+#include "bm_linalg.cuh"
 
 using namespace bm;
 
@@ -82,10 +83,15 @@ struct bm_ctx {
   // tridiagonal eigenvectors eZ, 1/norms eZn, polish matrix eC, deviation eDev
   int eig_ok = 0;            // a 16-CTA cluster can be launched on this device
   double *eD = nullptr, *eE = nullptr, *eTau = nullptr, *eV = nullptr, *eZ = nullptr, *eZn = nullptr,
-         *eC = nullptr, *eDev = nullptr, *eLam = nullptr, *eGm = nullptr;
+         *eC = nullptr, *eU2 = nullptr, *eDev = nullptr, *eLam = nullptr, *eGm = nullptr, *eT = nullptr;
+  long long* eProf = nullptr;   // BM_EIG_DEBUG: phase clocks of k_sytrd_fused
   double* h_dev = nullptr;   // pinned
   int* eig_status = nullptr; // raised by a bounded mbarrier wait of the cluster exchange that timed out
   long long eig_fast = 0, eig_fallback = 0;
+  int trivec3 = 1;              // 1: k_tri_vectors3 (three-term pivots), 0: k_tri_vectors (qd form; BM_TRIVEC=qd)
+  int wy_back = 1;              // 1: blocked compact-WY back-transformation (k_wy_T + k_wy_apply), 0: k_apply_reflectors (BM_BACKTRANSFORM=warp)
+  int sytrd_fused = 2;          // 2: k_sytrd_cluster (default, 1.21 ms at n=512), 0: the same with ONE polling warp (BM_SYTRD=onepoll, 1.22 ms),
+                                // 1: k_sytrd_fused (fused register pass; BM_SYTRD=fused, 1.34 ms) -- both measured slower, kept for the record
   int eig_debug = 0;         // BM_EIG_DEBUG=1: per-level stage times of the on-chip split on stderr
   std::vector<std::pair<const char*, cudaEvent_t>> dbg_ticks;
   int eig_prof = 0; cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; float eig_ms[5] = {0, 0, 0, 0, 0};
@@ -93,6 +99,9 @@ struct bm_ctx {
   double *psi = nullptr, *winv = nullptr, *lnpsi = nullptr;
   double* ws = nullptr; int ws_slots = 0;
   double *partZ = nullptr, *part2 = nullptr, *scal = nullptr;
+  int nZ = 0;                  // number of valid partials in partZ (set by merge_bond)
+  double* psi_part = nullptr; int psi_part_cap = 0;    // per-CTA [sum ln|psi|, #zero psi] of k_psi
+  cudaEvent_t ev_sync = nullptr;   // host waits (spinning) on this event instead of a blocking stream synchronise
   double* h_scal = nullptr; int* h_iscal = nullptr;   // pinned
   double* stage = nullptr; size_t stage_cap = 0;      // device staging for host<->device tensor moves
   int last_k = -1; int last_B = 0; const int* last_ids = nullptr;
@@ -198,13 +207,53 @@ int set_func_attrs(bm_ctx* c) {
 }
 
 
+// ---- own DMMA GEMM (bm_linalg.cuh): row-major C[m][n] = alpha * sum_k A(m,k) B(n,k) + beta * Cin[m][n] -------------
+// ak: A[m*lda + k] (else A[k*lda + m]);  bk: B[n*ldb + k] (else B[k*ldb + n]).  sym: C = A A^T, upper tiles mirrored.
+struct GemmBatch { int count = 1, bdiv = 1; long long sAhi = 0, sAlo = 0, sBhi = 0, sBlo = 0, sChi = 0, sClo = 0; };
+int gemm(bm_ctx* c, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
+         const double* B, long long ldb, double beta, const double* Cin, double* C, long long ldc, bool sym = false,
+         const GemmBatch& gb = GemmBatch(), double* sumsq = nullptr) {
+  if (M <= 0 || N <= 0) return BM_OK;
+  GemmParams P{};
+  P.A = A; P.lda = lda; P.B = B; P.ldb = ldb; P.Cin = Cin; P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
+  P.alpha = alpha; P.beta = beta; P.bdiv = gb.bdiv;
+  P.sAhi = gb.sAhi; P.sAlo = gb.sAlo; P.sBhi = gb.sBhi; P.sBlo = gb.sBlo; P.sChi = gb.sChi; P.sClo = gb.sClo;
+  P.sym = sym ? 1 : 0; P.sumsq = sumsq;
+  auto even64 = [](long long v) { return (v & 1) == 0; };
+  P.align16 = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && even64(lda) && even64(ldb) && even64(gb.sAhi) && even64(gb.sAlo) &&
+              even64(gb.sBhi) && even64(gb.sBlo);
+  const int tm = (M + GM_T - 1) / GM_T, tn = (N + GM_T - 1) / GM_T;
+  dim3 grid = sym ? dim3(tn * (tn + 1) / 2, 1, gb.count) : dim3(tn, tm, gb.count);
+  if (ak && bk) k_dgemm<true, true><<<grid, GM_THREADS, 0, c->stream>>>(P);
+  else if (ak && !bk) k_dgemm<true, false><<<grid, GM_THREADS, 0, c->stream>>>(P);
+  else if (!ak && !bk) k_dgemm<false, false><<<grid, GM_THREADS, 0, c->stream>>>(P);
+  else k_dgemm<false, true><<<grid, GM_THREADS, 0, c->stream>>>(P);
+  c->launches++;
+  KCHECK();
+  return BM_OK;
+}
+#define GEMM(...)                                          \
+  do {                                                     \
+    int r_ = gemm(c, __VA_ARGS__);                         \
+    if (r_ != BM_OK) return r_;                            \
+  } while (0)
+
+
 // ---- on-chip symmetric eigensolver (bm_eig.cuh) -----------------------------------------------------------------
+constexpr int DEV_SLOTS = 16;      // eDev / h_dev: one per Gram level (<= 8), [8] cross-level polish, [9] second round
 constexpr int BM_EIG_UNAVAILABLE = -1;   // internal: cluster launch refused, use cuSOLVER
 int eig_setup(bm_ctx* c) {
   c->eig_ok = 0;
-  if (cudaFuncSetAttribute(k_sytrd_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_sytrd_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sytrd_cluster<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
     cudaGetLastError();
     return BM_OK;                 // no 16-CTA clusters on this device: cuSOLVER path only
+  }
+  if (const char* v = std::getenv("BM_SYTRD")) c->sytrd_fused = !std::strcmp(v, "fused") ? 1 : (!std::strcmp(v, "onepoll") ? 0 : 2);
+  if (cudaFuncSetAttribute(k_sytrd_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sytrd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SytrdFusedSmem)) != cudaSuccess) {
+    cudaGetLastError();
+    if (c->sytrd_fused == 1) c->sytrd_fused = 2;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(EIG_CL); cfg.blockDim = dim3(EIG_NT); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
@@ -213,16 +262,21 @@ int eig_setup(bm_ctx* c) {
   at[0].val.clusterDim.x = EIG_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int ncl = 0;
-  if (cudaOccupancyMaxActiveClusters(&ncl, k_sytrd_cluster, &cfg) != cudaSuccess) { cudaGetLastError(); return BM_OK; }
+  if (cudaOccupancyMaxActiveClusters(&ncl, k_sytrd_cluster<true>, &cfg) != cudaSuccess) { cudaGetLastError(); return BM_OK; }
   if (ncl < 1) return BM_OK;
   const size_t N = EIG_NMAX;
-  DALLOC(c->eD, N); DALLOC(c->eE, N); DALLOC(c->eTau, N); DALLOC(c->eLam, N); DALLOC(c->eZn, N); DALLOC(c->eDev, 2); DALLOC(c->eGm, 8 * (N / REFL_CHUNK + 1));
-  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N); DALLOC(c->eig_status, 1);
+  DALLOC(c->eD, N); DALLOC(c->eE, N); DALLOC(c->eTau, N); DALLOC(c->eLam, N); DALLOC(c->eZn, N); DALLOC(c->eDev, DEV_SLOTS); DALLOC(c->eU2, N * N); DALLOC(c->eGm, 8 * (N / REFL_CHUNK + 1)); DALLOC(c->eT, (N / WY_B + 1) * WY_B * WY_B);
+  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N); DALLOC(c->eig_status, 1); DALLOC(c->eProf, 24);
   CU(cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->eV, 0, N * EIG_LDV * sizeof(double), c->stream));
   CU(cudaFuncSetAttribute(k_tri_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM));
+  CU(cudaFuncSetAttribute(k_tri_vectors3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM));
+  if (const char* v = std::getenv("BM_TRIVEC")) c->trivec3 = std::strcmp(v, "qd") != 0;
   CU(cudaFuncSetAttribute(k_apply_reflectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REFL_SMEM));
-  CU(cudaMallocHost((void**)&c->h_dev, 2 * sizeof(double)));
+  CU(cudaFuncSetAttribute(k_wy_T, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wy_T_smem_bytes(EIG_NMAX)));
+  CU(cudaFuncSetAttribute(k_wy_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wya_smem_bytes(EIG_NMAX)));
+  if (const char* v = std::getenv("BM_BACKTRANSFORM")) c->wy_back = std::strcmp(v, "warp") != 0;
+  CU(cudaMallocHost((void**)&c->h_dev, DEV_SLOTS * sizeof(double)));
   c->eig_ok = 1;
   if (const char* dbg = std::getenv("BM_EIG_DEBUG")) c->eig_debug = std::atoi(dbg);
   if (c->eig_debug) for (auto& ev : c->eig_ev) CU(cudaEventCreate(&ev));
@@ -232,7 +286,9 @@ int eig_setup(bm_ctx* c) {
 // eigenvalues of the symmetric n x n matrix G (device, ld) -> c->eLam (device, ascending).  Reflectors stay in eV/eTau.
 int eig_values(bm_ctx* c, const double* G, int ld, int n) {
   if (c->eig_prof) cudaEventRecord(c->eig_ev[0], c->stream);
-  k_sytrd_cluster<<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status);
+  if (c->sytrd_fused == 1) k_sytrd_fused<<<EIG_CL, EIG_NT, sizeof(SytrdFusedSmem), c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status, c->eig_debug ? c->eProf : nullptr);
+  else if (c->sytrd_fused == 2) k_sytrd_cluster<false><<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status);
+  else k_sytrd_cluster<true><<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status);
   if (cudaPeekAtLastError() != cudaSuccess) {      // the cluster cannot be placed after all (e.g. a partitioned GPU):
     cudaGetLastError();                            // stop using the on-chip path, the caller falls back to cuSOLVER
     c->eig_ok = 0;
@@ -271,50 +327,68 @@ void dbg_flush(bm_ctx* c) {
   std::fprintf(stderr, "%s\n", line.c_str());
 }
 
-// cuBLAS picks (and lazily loads, ~10 ms the first time) a kernel per GEMM shape: the column counts of the polish
-// and deflation GEMMs are therefore padded with zero columns to multiples of 64, and those shapes are warmed once.
-inline int pad64(int m, int cap) { return std::min((m + 63) & ~63, cap); }
+// Host waits for everything enqueued so far by spinning on an event (a blocking cudaStreamSynchronize costs tens of
+// microseconds of wake-up latency, twice per two-site step).
+int wait_stream(bm_ctx* c) {
+  CU(cudaEventRecord(c->ev_sync, c->stream));
+  cudaError_t e;
+  while ((e = cudaEventQuery(c->ev_sync)) == cudaErrorNotReady) {}
+  if (e != cudaSuccess) return fail(c, BM_ECUDA, std::string("device error: ") + cudaGetErrorString(e));
+  return BM_OK;
+}
+#define WAIT()                                             \
+  do {                                                     \
+    int r_ = wait_stream(c);                               \
+    if (r_ != BM_OK) return r_;                            \
+  } while (0)
 
-// Newton-Schulz orthonormality polish of U (n x m, ldu == n, room for `cap` >= m columns):
-// U <- U (1.5 I - 0.5 U^T U), at most two rounds.  h_dev[round] = max |U^T U - I| measured BEFORE that round (the
-// round squares it).  Columns m .. pad64(m) of U are zeroed.  Synchronises the stream.
-int polish_columns(bm_ctx* c, int n, int m, double* U, int ldu, int cap) {
-  const double one = 1.0, zero = 0.0;
-  const int mp = ldu == n ? pad64(m, cap) : m;
-  if (mp > m) CU(cudaMemsetAsync(U + (size_t)m * ldu, 0, (size_t)(mp - m) * ldu * sizeof(double), c->stream));
-  c->h_dev[0] = c->h_dev[1] = DBL_MAX;
-  for (int round = 0; round < 2; ++round) {
-    dbg_tick(c, "[polish");
-    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mp, mp, n, &one, U, ldu, U, ldu, &zero, c->eC, mp));
-    dbg_tick(c, "UtU");
-    CU(cudaMemsetAsync(c->eDev + round, 0, sizeof(double), c->stream));
-    k_polish_coef<<<POLISH_BLOCKS, 256, 0, c->stream>>>(c->eC, mp, mp, m, c->eDev + round);
-    c->launches++;
-    KCHECK();
-    dbg_tick(c, "coef");
-    LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, n, mp, mp, &one, U, ldu, c->eC, mp, &zero, c->eZ, n));
-    dbg_tick(c, "UC");
-    CU(cudaMemcpy2DAsync(U, (size_t)ldu * sizeof(double), c->eZ, (size_t)n * sizeof(double), (size_t)n * sizeof(double), mp, cudaMemcpyDeviceToDevice, c->stream));
-    dbg_tick(c, "copy]");
-    CU(cudaMemcpyAsync(c->h_dev + round, c->eDev + round, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (round == 0 && c->h_dev[0] < 1e-8) break;      // deviation after the polish ~ square of it: done
-    if (round == 0 && !(c->h_dev[0] < 1e-3)) break;   // hopeless (degenerate cluster / NaN): caller falls back
-  }
+// One Newton-Schulz round  Uout <- Uin (1.5 I - 0.5 Uin^T Uin)  (n x m column-major; Uout != Uin).  The deviation
+// max |Uin^T Uin - I| measured BEFORE the round lands in c->eDev[slot] (device): the caller checks it at its next
+// synchronisation (the round squares it).  Nothing here synchronises.
+int polish_round(bm_ctx* c, int n, int m, const double* Uin, int ldin, double* Uout, int ldout, int slot) {
+  dbg_tick(c, "[polish");
+  // row-major view: Urm (m x n) holds one eigenvector per row.  C = Urm Urm^T (symmetric, m x m)
+  GEMM(true, true, m, m, n, 1.0, Uin, ldin, Uin, ldin, 0.0, nullptr, c->eC, m, true);
+  dbg_tick(c, "UtU");
+  k_polish_coef<<<std::min(POLISH_BLOCKS, m), 256, 0, c->stream>>>(c->eC, m, m, c->eDev + slot);
+  c->launches++;
+  KCHECK();
+  dbg_tick(c, "coef");
+  // Uout_rm = C Urm   (C symmetric): out[j][r] = sum_k C[j][k] Urm[k][r]
+  GEMM(true, false, m, n, m, 1.0, c->eC, m, Uin, ldin, 0.0, nullptr, Uout, ldout);
+  dbg_tick(c, "UC]");
   return BM_OK;
 }
 
-// eigenvectors of the m largest eigenvalues (descending) -> U (n x m, ldu), one Newton-Schulz polish; h_dev[0] =
-// max |U^T U - I| BEFORE the polish (the result deviates by its square).  Synchronises the stream.
-int eig_vectors(bm_ctx* c, int n, int m, double* U, int ldu, int cap) {
-  k_tri_vectors<<<(m + TV_EIG - 1) / TV_EIG, 32, TV_SMEM, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eZ, c->eZn);
+// eigenvectors of the m largest eigenvalues (descending) -> U (n x m, ldu) after ONE Newton-Schulz round; the deviation
+// from orthonormality before that round is left in c->eDev[slot].  Nothing here synchronises.
+int eig_vectors(bm_ctx* c, int n, int m, double* U, int ldu, int slot) {
+  if (c->trivec3) k_tri_vectors3<<<(m + TV_EIG - 1) / TV_EIG, 32, TV_SMEM, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eZ, c->eZn);
+  else k_tri_vectors<<<(m + TV_EIG - 1) / TV_EIG, 32, TV_SMEM, c->stream>>>(c->eD, c->eE, n, c->eLam, m, c->eZ, c->eZn);
   if (c->eig_prof) cudaEventRecord(c->eig_ev[3], c->stream);
-  if (n > 2) k_refl_gram<<<(n - 2 + REFL_CHUNK - 1) / REFL_CHUNK, 128, 0, c->stream>>>(c->eV, n, c->eGm);
-  k_apply_reflectors<<<(m + REFL_WARPS - 1) / REFL_WARPS, REFL_WARPS * 32, REFL_SMEM, c->stream>>>(c->eV, c->eTau, c->eGm, n, c->eZ, c->eZn, m, U, ldu);
+  double* raw = c->eU2;                                     // back-transformed, not yet polished (n x m, ld n)
+  if (c->wy_back) {
+    const int nrefl = n > 2 ? n - 2 : 0;
+    k_wy_apply<<<(m + WYA_NC - 1) / WYA_NC, WYA_THREADS, wya_smem_bytes(n), c->stream>>>(c->eV, EIG_LDV, c->eT, n, nrefl, c->eZ, c->eZn, m, raw, n);
+  } else {
+    if (n > 2) k_refl_gram<<<(n - 2 + REFL_CHUNK - 1) / REFL_CHUNK, 128, 0, c->stream>>>(c->eV, n, c->eGm);
+    k_apply_reflectors<<<(m + REFL_WARPS - 1) / REFL_WARPS, REFL_WARPS * 32, REFL_SMEM, c->stream>>>(c->eV, c->eTau, c->eGm, n, c->eZ, c->eZn, m, raw, n);
+  }
   if (c->eig_prof) cudaEventRecord(c->eig_ev[4], c->stream);
-  c->launches += 2;
+  c->launches += 3;
   KCHECK();
-  return polish_columns(c, n, m, U, ldu, cap);
+  return polish_round(c, n, m, raw, n, U, ldu, slot);
+}
+
+// compact-WY factors of the reflectors left by eig_values (independent of the eigenvalues: enqueued while the host
+// is still waiting for them)
+int eig_wy_factors(bm_ctx* c, int n) {
+  const int nrefl = n > 2 ? n - 2 : 0;
+  if (!c->wy_back || nrefl == 0) return BM_OK;
+  k_wy_T<<<(nrefl + WY_B - 1) / WY_B, 1024, wy_T_smem_bytes(n), c->stream>>>(c->eV, EIG_LDV, c->eTau, n, nrefl, c->eT);
+  c->launches++;
+  KCHECK();
+  return BM_OK;
 }
 
 // persistent panel kernels: one CTA per resident slot, never more CTAs than 16-row work units
@@ -494,23 +568,14 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
     LIB(cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)mA, c->Gq, (int)mA, c->lam, &lw));
     if ((size_t)lw > c->lwork) { DALLOC(c->work, (size_t)lw); c->lwork = (size_t)lw; }
   }
-  if (c->eig_ok && mA <= EIG_NMAX) {   // load the cuBLAS kernels of the split's GEMM shapes at full bond dimension
-    const int pp = (int)mA;
-    const double one = 1.0, zero = 0.0;
-    CU(cudaMemsetAsync(c->U, 0, mA * mA * sizeof(double), c->stream));
-    CU(cudaMemsetAsync(c->W, 0, mA * mA * sizeof(double), c->stream));
-    CU(cudaMemsetAsync(c->Yb[0], 0, mA * mA * sizeof(double), c->stream));
-    LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, pp, pp, pp, &one, c->W, pp, c->W, pp, &zero, c->Gq, pp));
-    for (int mp = 64; mp <= pp; mp += 64) {
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mp, mp, pp, &one, c->U, pp, c->U, pp, &zero, c->eC, mp));
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, pp, mp, mp, &one, c->U, pp, c->eC, mp, &zero, c->eZ, pp));
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, pp, mp, pp, &one, c->W, pp, c->U, pp, &zero, c->Tmp, pp));
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_T, pp, pp, mp, &one, c->Tmp, pp, c->U, pp, &one, c->Yb[0], pp));
-    }
-    CU(cudaStreamSynchronize(c->stream));
+  {
+    const int tcap = (c->Dcap + GM_T - 1) / GM_T;
+    DALLOC(c->partZ, std::max(RED_BLOCKS, c->d * c->d * tcap * tcap)); DALLOC(c->part2, UPD_BLOCKS * 4); DALLOC(c->scal, 8);
+    c->psi_part_cap = std::max(c->panel_ctas, 1024);
+    DALLOC(c->psi_part, 2 * c->psi_part_cap);
+    CU(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
   }
-  DALLOC(c->partZ, RED_BLOCKS); DALLOC(c->part2, RED_BLOCKS * 4); DALLOC(c->scal, 8);
-  CU(cudaMallocHost((void**)&c->h_scal, 8 * sizeof(double)));
+  CU(cudaMallocHost((void**)&c->h_scal, 16 * sizeof(double)));
   CU(cudaMallocHost((void**)&c->h_iscal, 4 * sizeof(int)));
   CU(cudaMemsetAsync(c->scal, 0, 8 * sizeof(double), c->stream));
   return BM_OK;
@@ -524,8 +589,8 @@ int bm_destroy(bm_ctx* c) {
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eDev, c->eLam, c->eGm, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
-                  c->ws, c->partZ, c->part2, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
+                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -536,6 +601,7 @@ int bm_destroy(bm_ctx* c) {
   for (auto& ev : c->eig_ev) if (ev) cudaEventDestroy(ev);
   for (auto& tk : c->dbg_ticks) cudaEventDestroy(tk.second);
   if (c->tev[0]) { cudaEventDestroy(c->tev[0]); cudaEventDestroy(c->tev[1]); }
+  if (c->ev_sync) cudaEventDestroy(c->ev_sync);
   if (c->gesvdj) cusolverDnDestroyGesvdjInfo(c->gesvdj);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
   if (c->cublas) cublasDestroy(c->cublas);
@@ -582,10 +648,30 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
     CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
+    if (c->eig_debug && c->sytrd_fused == 1) {
+      long long hp[24];
+      CU(cudaMemcpy(hp, c->eProf, sizeof hp, cudaMemcpyDeviceToHost));
+      const double cols = n > 2 ? n - 2 : 1;
+      std::fprintf(stderr, "[bm sytrd phases, cycles/column, n=%d] warp0: pass %.0f scalars %.0f rowsum+msg %.0f bar %.0f send %.0f wait %.0f next %.0f bar %.0f | "
+                   "warp15: pass %.0f scalars %.0f rowsum+msg %.0f bar %.0f - %.0f wait %.0f next %.0f bar %.0f\n", n,
+                   hp[0] / cols, hp[1] / cols, hp[2] / cols, hp[3] / cols, hp[4] / cols, hp[5] / cols, hp[6] / cols, hp[7] / cols,
+                   hp[8] / cols, hp[9] / cols, hp[10] / cols, hp[11] / cols, hp[12] / cols, hp[13] / cols, hp[14] / cols, hp[15] / cols);
+      std::fprintf(stderr, "[bm sytrd send sub-phases, cumulative cycles/column] dot-sum %.0f fence %.0f syncwarp %.0f\n", hp[16] / cols, hp[17] / cols, hp[18] / cols);
+    }
     if (m > 0) {
-      r = eig_vectors(c, n, m, c->Tmp, n, n);
+      r = eig_wy_factors(c, n);
       if (r != BM_OK) return r;
+      CU(cudaMemsetAsync(c->eDev, 0, DEV_SLOTS * sizeof(double), c->stream));
+      r = eig_vectors(c, n, m, c->Tmp, n, 0);
+      if (r != BM_OK) return r;
+      CU(cudaMemcpyAsync(c->h_dev, c->eDev, DEV_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      WAIT();
       dev0 = c->h_dev[0];
+      if (!(dev0 < 1e-8) && dev0 < 1e-3) {     // second Newton-Schulz round (the first squares the deviation)
+        r = polish_round(c, n, m, c->Tmp, n, c->eU2, n, 9);
+        if (r != BM_OK) return r;
+        CU(cudaMemcpyAsync(c->Tmp, c->eU2, (size_t)n * m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      }
     }
   } else {
     int lw = 0;
@@ -792,27 +878,21 @@ int bm_grad_dims(bm_ctx* c, int k, int* rows, int* ld, int* Dl, int* Dr, int* ld
   return BM_OK;
 }
 
-// merge: A[(p,a),(q,c)] = sum_b M_k[a,b,p] M_{k+1}[b,c,q]  (TNutils.py:1526) — plain library GEMMs; also the
-// partial sums of Z = <A,A>
+// merge: A[(p,a),(q,c)] = sum_b M_k[a,b,p] M_{k+1}[b,c,q]  (TNutils.py:1526) — one batched k_dgemm launch over the
+// d*d pixel pairs, which also leaves the per-CTA partial sums of Z = <A,A> in partZ
 static int merge_bond(bm_ctx* c, int k) {
   const int d = c->d;
   const int Dl = c->sDl[k], chi0 = c->sDr[k], Dr = c->sDr[k + 1];
-  const int ldx = even(chi0), ldr = even(Dr), ldA = d * ldr, rows = d * Dl;
-  {
-    Timer t_(c, 4);
-    const double one = 1.0, zero = 0.0;
-    for (int p = 0; p < d; ++p)
-      for (int q = 0; q < d; ++q) {
-        const double* X = c->Lf(k) + (size_t)p * ldx;        // [a][p][b], ld = d*ldx
-        const double* Y = c->Rf(k + 1) + (size_t)q * ldx;    // [c][q][b], ld = d*ldx
-        double* C = c->Aint + (size_t)p * Dl * ldA + (size_t)q * ldr;
-        LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, Dr, Dl, chi0, &one, Y, d * ldx, X, d * ldx, &zero, C, ldA));
-      }
-  }
-  k_sumsq<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, rows, ldA, Dr, ldr, c->partZ);
-  c->launches++;
-  KCHECK();
-  return BM_OK;
+  const int ldx = even(chi0), ldr = even(Dr), ldA = d * ldr;
+  Timer t_(c, 4);
+  if (ldr != Dr) CU(cudaMemsetAsync(c->Aint, 0, (size_t)d * Dl * ldA * sizeof(double), c->stream));   // pad columns
+  GemmBatch gb;
+  gb.count = d * d; gb.bdiv = d;
+  gb.sAhi = ldx; gb.sBlo = ldx; gb.sChi = (long long)Dl * ldA; gb.sClo = ldr;
+  const int tm = (Dl + GM_T - 1) / GM_T, tn = (Dr + GM_T - 1) / GM_T;
+  c->nZ = tm * tn * d * d;
+  return gemm(c, true, true, Dl, Dr, chi0, 1.0, c->Lf(k), (long long)d * ldx, c->Rf(k + 1), (long long)d * ldx, 0.0, nullptr,
+              c->Aint, ldA, false, gb, c->partZ);
 }
 
 int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double* S_dev) {
@@ -823,8 +903,8 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
   r = bm_env_build(c, k);
   if (r != BM_OK) return r;
   const int d = c->d, G = d * d, N = c->N;
-  const int Dl = c->sDl[k], chi0 = c->sDr[k], Dr = c->sDr[k + 1];
-  const int ldx = even(chi0), ldr = even(Dr), ldA = d * ldr, rows = d * Dl;
+  const int Dl = c->sDl[k], Dr = c->sDr[k + 1];
+  const int ldr = even(Dr), ldA = d * ldr, rows = d * Dl;
 
   r = merge_bond(c, k);
   if (r != BM_OK) return r;
@@ -833,18 +913,21 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
   const int* perm; const int* goff; const int* h_goff; int B;
   if (mask_host) {
     REQUIRE(n_mask > 0 && n_mask <= N, "bm_step_grad: bad minibatch size");
+    for (int i = 0; i < n_mask; ++i) REQUIRE(mask_host[i] >= 0 && mask_host[i] < N, "bm_step_grad: minibatch sample id out of range");
     CU(cudaMemcpyAsync(c->bmask, mask_host, (size_t)n_mask * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     k_build_perm<<<1, 256, 0, c->stream>>>(c->phys + (size_t)k * N, N, d, 1, c->bmask, n_mask, c->bperm, c->bgoff, N);
     c->launches++;
     c->h_bgoff.resize(G + 1);
     CU(cudaMemcpyAsync(c->h_bgoff.data(), c->bgoff, (G + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    WAIT();
     perm = c->bperm; goff = c->bgoff; h_goff = c->h_bgoff.data(); B = n_mask;
   } else {
     perm = c->perm + (size_t)k * N; goff = c->goff + (size_t)k * (G + 1); h_goff = c->h_goff.data() + (size_t)k * (G + 1); B = N;
   }
 
-  // ---- psi
+  // ---- psi (+ per-CTA partial sums of ln|psi| and of the zero count)
+  const int psi_grid = panel_grid(c, B, G);
+  REQUIRE(psi_grid <= c->psi_part_cap, "bm_step_grad: psi partial buffer too small");
   {
     Timer t_(c, 1);
     PsiParams P{};
@@ -853,8 +936,8 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     P.A = c->Aint; P.ldA = ldA;
     P.gs = GroupSpec{perm, goff, G, d, (long long)Dl * ldA, (long long)ldr};
     P.cumeL = c->cume_slot(k); P.cumeR = c->cume_slot(k + 2);
-    P.psi = c->psi; P.winv = c->winv; P.lnpsi = c->lnpsi;
-    k_psi<<<panel_grid(c, B, G), NTHREADS, PANEL_SMEM, c->stream>>>(P);
+    P.psi = c->psi; P.winv = c->winv; P.lnpsi = c->lnpsi; P.part = c->psi_part;
+    k_psi<<<psi_grid, NTHREADS, PANEL_SMEM, c->stream>>>(P);
     c->launches++;
     KCHECK();
   }
@@ -896,7 +979,6 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     }
     if (c->peer_world > 1) {
       // fused: local split reduction + cross-GPU sum over NVLink peer memory, straight into S_dev
-      k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, c->tail_local);
       PeerParams PP{};
       for (int r = 0; r < c->peer_world; ++r) {
         PP.base[r] = c->peer_base[r];
@@ -905,12 +987,12 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
       PP.world = c->peer_world; PP.rank = c->peer_rank; PP.step = ++c->peer_step; PP.slot = (int)(c->peer_step & 1);
       PP.slot_elems = (long long)c->peer_slot_elems;
       Timer t_(c, 3);
-      k_grad_reduce_peer<<<PEER_CHUNKS, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, c->tail_local, PP, S_dev, c->tf_status);
+      k_grad_reduce_peer<<<PEER_CHUNKS, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, c->psi_part, psi_grid, PP, S_dev, c->tf_status);
     } else {
-      { Timer t_(c, 3); k_grad_reduce<<<148 * 4, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, S_dev); }
-      k_lnpsi_reduce<<<1, 1024, 0, c->stream>>>(c->lnpsi, c->psi, perm, B, S_dev + (size_t)rows * ldA);
+      Timer t_(c, 3);
+      k_grad_reduce<<<148 * 4, 256, 0, c->stream>>>(c->ws, P.ws_stride, goff, kchunk, d, Dl, Dr, ldA, ldr, S_dev, c->psi_part, psi_grid);
     }
-    c->launches += 3;
+    c->launches += 2;
     KCHECK();
   }
   c->last_k = k; c->last_B = B; c->last_ids = perm;
@@ -927,20 +1009,138 @@ static int run_svd_gesvdj(bm_ctx* c, int mA, int nA) {
   return BM_OK;
 }
 
-// Gram split: eigen-decomposition (cuSOLVER syevd) of the Gram matrix on the ISOMETRIC side, so that factor is
-// orthonormal to machine precision; the absorbed factor is obtained by projection (no division by s).
-// Small singular values (below sqrt(tau) of the level's largest) are recovered by deflating the resolved
-// subspace and repeating on the remainder, which keeps the relative cutoff rule (1e-10) exact.
+// quimb split rule on descending singular values (oracle/born_oracle.py::split): keep s_i > cutoff * s_0, at least one,
+// at most max_bond
+static int chi_rule(const std::vector<double>& sv, double cutoff, int max_bond) {
+  int chi;
+  if (cutoff > 0.0) {
+    chi = 0;
+    for (double x : sv) if (x > cutoff * sv[0]) ++chi;
+    chi = std::max(chi, 1);
+    if (max_bond > 0) chi = std::min(chi, max_bond);
+  } else chi = max_bond > 0 ? std::min(max_bond, (int)sv.size()) : (int)sv.size();
+  return chi;
+}
+
+// Gram split: eigen-decomposition of the Gram matrix on the ISOMETRIC side, so that factor is orthonormal to machine
+// precision; the absorbed factor is obtained by projection (no division by s).  Small singular values (below sqrt(tau)
+// of the level's largest) are recovered by deflating the resolved subspace and repeating on the remainder, which keeps
+// the relative cutoff rule (1e-10) exact.
 //   c->W holds Y = (q x p, column-major): A^T when the left factor is the isometry (p = mA), A otherwise (p = nA).
-//   Outputs: isometry (p x r) and absorbed factor (q x chi) in c->U / c->V, singular values in c->h_s, chi.
-static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond, double cutoff, int* chi_out, double* trunc_out) {
-  Timer t_(c, 5);
-  constexpr double TAU = 1e-7;   // level-0 values down to 3e-4 s_0: rel. error <= eps*n/(2 tau) ~ 2.5e-7
-  const int p = going_right ? mA : nA, q = going_right ? nA : mA;
-  double* iso = going_right ? c->U : c->V;
-  double* absb = going_right ? c->V : c->U;
-  const int rmin = std::min(mA, nA);
-  const int need = std::min(max_bond > 0 ? max_bond : rmin, rmin);
+//   Outputs: isometry (p x chi) and absorbed factor (q x chi) in c->U / c->V, singular values in c->h_s, chi.
+constexpr double GRAM_TAU = 1e-7;   // level-0 values down to 3e-4 s_0: rel. error <= eps*n/(2 tau) ~ 2.5e-7
+
+// ---- fast path: on-chip eigensolver (bm_eig.cuh).  A level resolves the eigenvalues above TAU of its largest; the
+// resolved directions are then projected out of Y (Y <- Y - (Y U) U^T, on Y so that the small singular values keep
+// their relative accuracy) and the next level runs on the Gram matrix of the remainder.
+// The host synchronises ONCE per level (it needs the eigenvalues to decide what to keep); the orthonormality checks of
+// the eigenvectors stay on the device (c->eDev) and are verified by the caller at its final synchronisation
+// (gram_fast_verified): *ok == false means "use the cuSOLVER levels instead".
+static int run_svd_gram_fast(bm_ctx* c, int p, int q, double* iso, double* absb, int need, int rmin, int max_bond, double cutoff,
+                             int* chi_out, double* trunc_out, bool* ok_out) {
+  std::vector<double>& sv = c->h_s;
+  sv.clear();
+  *ok_out = false;
+  const double* Ycur = c->W;
+  bool finished = false;
+  int ncols = 0, chi = 0, flev = 0;
+  double sigma0sq = 0.0;
+  CU(cudaMemsetAsync(c->eDev, 0, DEV_SLOTS * sizeof(double), c->stream));
+  while (!finished) {
+    ++flev;
+    dbg_tick(c, "[level");
+    GEMM(true, true, p, p, q, 1.0, Ycur, q, Ycur, q, 0.0, nullptr, c->Gq, p, true);   // G = Y^T Y (Y col-major q x p)
+    dbg_tick(c, "gram");
+    c->eig_prof = c->eig_debug;
+    int r = eig_values(c, c->Gq, p, p);
+    if (r == BM_EIG_UNAVAILABLE) return BM_OK;
+    if (r != BM_OK) return r;
+    CU(cudaMemcpyAsync(c->h_lam, c->eLam, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev_sync, c->stream));
+    r = eig_wy_factors(c, p);                                  // runs while the host waits for the eigenvalues
+    if (r != BM_OK) return r;
+    {
+      cudaError_t e;
+      while ((e = cudaEventQuery(c->ev_sync)) == cudaErrorNotReady) {}
+      if (e != cudaSuccess) return fail(c, BM_ECUDA, std::string("device error: ") + cudaGetErrorString(e));
+    }
+    if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd: cluster exchange timed out");
+    const double* lam = c->h_lam;
+    const double lmax = lam[p - 1];
+    const int peff = p - ncols;                              // the ncols smallest are the projected-out directions
+    bool finite = true;
+    for (int j = 0; j < p; ++j) finite = finite && std::isfinite(lam[j]);
+    if (!finite) return BM_OK;                               // e.g. denormal trailing columns: let LAPACK-style code decide
+    if (flev == 1) {
+      if (!(lmax > 0.0)) return BM_OK;
+      sigma0sq = lmax;
+    }
+    int kkeep = 0;
+    if (lmax > 0.0) while (kkeep < peff && lam[p - 1 - kkeep] > GRAM_TAU * lmax) ++kkeep;
+    const int rest = peff - kkeep;
+    const bool done = (ncols + kkeep >= need) || rest == 0 || !(lmax > 0.0) || (GRAM_TAU * lmax <= cutoff * cutoff * sigma0sq);
+    if (!done && flev >= 8) return BM_OK;
+    const int npush = done ? peff : kkeep;
+    for (int j = 0; j < npush; ++j) sv.push_back(std::sqrt(std::max(lam[p - 1 - j], 0.0)));
+    int nv = kkeep;
+    if (done) {
+      if ((int)sv.size() > rmin) sv.resize(rmin);
+      chi = chi_rule(sv, cutoff, max_bond);
+      nv = chi - ncols;
+      if (nv > kkeep) return BM_OK;                          // would need vectors of unresolved values
+      if (nv < 0) nv = 0;
+    }
+    if (nv > 0) {
+      // separation of the wanted eigenvalues (and of the last one from its lower neighbour)
+      double gap = DBL_MAX;
+      for (int j = 0; j < nv && j + 1 < p; ++j) gap = std::min(gap, lam[p - 1 - j] - lam[p - 2 - j]);
+      if (!(gap > 4.0 * DBL_EPSILON * lmax * 1e5)) return BM_OK;   // predicted loss of orthogonality > 1e-5
+      double* Ulev = iso + (size_t)ncols * p;
+      r = eig_vectors(c, p, nv, Ulev, p, flev - 1);
+      if (r != BM_OK) return r;
+      c->eig_prof = 0;
+      if (!done) {                                           // Y <- Y - (Y U) U^T
+        double* Yn = c->Yb[flev & 1];
+        dbg_tick(c, "[deflate");
+        // row-major views: Yrm (p x q, ld q), Urm (nv x p, ld p):  Tmp = Urm Yrm (nv x q);  Yn = Yrm - Urm^T Tmp
+        GEMM(true, false, nv, q, p, 1.0, Ulev, p, Ycur, q, 0.0, nullptr, c->Tmp, q);
+        dbg_tick(c, "YU");
+        GEMM(false, false, p, q, nv, -1.0, Ulev, p, c->Tmp, q, 1.0, Ycur, Yn, q);
+        dbg_tick(c, "Y-TUt]");
+        Ycur = Yn;
+      }
+      ncols += nv;
+    }
+    finished = done;
+  }
+  if (flev > 1 && chi > 1) {                                 // cross-level orthonormality: one more round over all columns
+    int r = polish_round(c, p, chi, iso, p, c->eU2, p, 8);
+    if (r != BM_OK) return r;
+    CU(cudaMemcpyAsync(iso, c->eU2, (size_t)p * chi * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  c->gram_levels = flev;
+  double t2 = 0.0;
+  for (size_t i = chi; i < sv.size(); ++i) t2 += sv[i] * sv[i];
+  *chi_out = chi; *trunc_out = std::sqrt(t2);
+  GEMM(true, false, chi, q, p, 1.0, iso, p, c->W, q, 0.0, nullptr, absb, q);   // absorbed^T = iso^T Y^T (row-major chi x q)
+  dbg_tick(c, "project");
+  CU(cudaMemcpyAsync(c->h_dev, c->eDev, DEV_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  *ok_out = true;
+  return BM_OK;
+}
+
+// after a synchronisation: did every Newton-Schulz round of the fast path start from a deviation small enough that
+// the polished columns are orthonormal to ~1e-14 ?   (h_dev slots: levels 0..7, [8] the cross-level round)
+static bool gram_fast_verified(const bm_ctx* c) {
+  for (int i = 0; i < c->gram_levels && i < 8; ++i) if (!(c->h_dev[i] < 1e-7)) return false;
+  if (c->gram_levels > 1 && !(c->h_dev[8] < 1e-7)) return false;
+  return true;
+}
+
+// cuSOLVER levels (svd='gram_syevd', n > 512, degenerate kept eigenvalues, failed orthonormality check)
+static int run_svd_gram_syevd(bm_ctx* c, int p, int q, double* iso, double* absb, int need, int rmin, int max_bond, double cutoff,
+                              int* chi_out, double* trunc_out) {
   const double one = 1.0, zero = 0.0;
   std::vector<double>& sv = c->h_s;
   sv.clear();
@@ -948,112 +1148,6 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
   const double* T = nullptr;
   int pl = p, lev = 0, yb = 0, tb = 0, ncols_out = 0;
   double sigma0sq = 0.0;
-  // ---- fast path: on-chip eigensolver (bm_eig.cuh), same level structure as the cuSOLVER path below.  A level
-  // resolves the eigenvalues above TAU of its largest; the resolved directions are then projected out of Y
-  // (Y <- Y - (Y U) U^T, on Y so that the small singular values keep their relative accuracy) and the next level runs
-  // on the Gram matrix of the remainder (same size; the projected-out directions reappear as zeros and are skipped).
-  // Falls back to cuSOLVER for n > 512, degenerate eigenvalues among the kept ones, or a failed orthonormality check.
-  if (c->svd_method == BM_SVD_GRAM && c->eig_ok && p <= EIG_NMAX && p >= 2) {
-    const double* Ycur = c->W;
-    bool ok = true, finished = false;
-    int ncols = 0, chi = 0, flev = 0;
-    while (ok && !finished) {
-      ++flev;
-      dbg_tick(c, "[level");
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, p, p, q, &one, Ycur, q, Ycur, q, &zero, c->Gq, p));
-      dbg_tick(c, "gram");
-      c->eig_prof = c->eig_debug;
-      int r = eig_values(c, c->Gq, p, p);
-      if (r == BM_EIG_UNAVAILABLE) { ok = false; break; }
-      if (r != BM_OK) return r;
-      CU(cudaMemcpyAsync(c->h_lam, c->eLam, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
-      const double* lam = c->h_lam;
-      const double lmax = lam[p - 1];
-      const int peff = p - ncols;                              // the ncols smallest are the projected-out directions
-      bool finite = true;
-      for (int j = 0; j < p; ++j) finite = finite && std::isfinite(lam[j]);
-      if (!finite) { ok = false; break; }                      // e.g. denormal trailing columns: let LAPACK-style code decide
-      if (flev == 1) {
-        if (!(lmax > 0.0)) { ok = false; break; }
-        sigma0sq = lmax;
-      }
-      int kkeep = 0;
-      if (lmax > 0.0) while (kkeep < peff && lam[p - 1 - kkeep] > TAU * lmax) ++kkeep;
-      const int rest = peff - kkeep;
-      const bool done = (ncols + kkeep >= need) || rest == 0 || !(lmax > 0.0) || (TAU * lmax <= cutoff * cutoff * sigma0sq);
-      if (!done && flev >= 8) { ok = false; break; }
-      const int npush = done ? peff : kkeep;
-      for (int j = 0; j < npush; ++j) sv.push_back(std::sqrt(std::max(lam[p - 1 - j], 0.0)));
-      int nv = kkeep;
-      if (done) {
-        if ((int)sv.size() > rmin) sv.resize(rmin);
-        if (cutoff > 0.0) {
-          for (double x : sv) if (x > cutoff * sv[0]) ++chi;
-          chi = std::max(chi, 1);
-          if (max_bond > 0) chi = std::min(chi, max_bond);
-        } else chi = max_bond > 0 ? std::min(max_bond, (int)sv.size()) : (int)sv.size();
-        nv = chi - ncols;
-        if (nv > kkeep) { ok = false; break; }                 // would need vectors of unresolved values
-        if (nv < 0) nv = 0;
-      }
-      if (nv > 0) {
-        // separation of the wanted eigenvalues (and of the last one from its lower neighbour)
-        double gap = DBL_MAX;
-        for (int j = 0; j < nv && j + 1 < p; ++j) gap = std::min(gap, lam[p - 1 - j] - lam[p - 2 - j]);
-        if (!(gap > 4.0 * DBL_EPSILON * lmax * 1e5)) { ok = false; break; }   // predicted loss of orthogonality > 1e-5
-        double* Ulev = iso + (size_t)ncols * p;
-        r = eig_vectors(c, p, nv, Ulev, p, p - ncols);
-        if (r != BM_OK) return r;
-        if (c->eig_debug) {
-          float f[4] = {0, 0, 0, 0};
-          for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&f[i], c->eig_ev[i], c->eig_ev[i + 1]);
-          std::fprintf(stderr, "[bm eig] level %d p=%d ncols=%d kkeep=%d nv=%d done=%d lmax=%.3e | sytrd %.3f eigvals %.3f readback+vectors %.3f reflectors %.3f ms | dev %.2e %.2e\n",
-                       flev, p, ncols, kkeep, nv, (int)done, lmax, f[0], f[1], f[2], f[3], c->h_dev[0], c->h_dev[1]);
-        }
-        c->eig_prof = 0;
-        const double devn = c->h_dev[0] < 1e-8 ? c->h_dev[0] * c->h_dev[0] : c->h_dev[1] * c->h_dev[1];
-        if (!(devn < 1e-13)) { ok = false; break; }
-        if (!done) {                                           // Y <- Y - (Y U) U^T
-          double* Yn = c->Yb[flev & 1];
-          const double mone = -1.0;
-          const int nvp = pad64(nv, p - ncols);                // the padding columns of Ulev are zero (polish_columns)
-          dbg_tick(c, "[deflate");
-          LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, q, nvp, p, &one, Ycur, q, Ulev, p, &zero, c->Tmp, q));
-          dbg_tick(c, "YU");
-          CU(cudaMemcpyAsync(Yn, Ycur, (size_t)q * p * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-          dbg_tick(c, "copy");
-          LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_T, q, p, nvp, &mone, c->Tmp, q, Ulev, p, &one, Yn, q));
-          dbg_tick(c, "Y-TUt]");
-          Ycur = Yn;
-        }
-        ncols += nv;
-      }
-      finished = done;
-    }
-    if (ok && flev > 1 && chi > 1) {                           // cross-level orthonormality: one more verified polish
-      int r = polish_columns(c, p, chi, iso, p, p);
-      if (r != BM_OK) return r;
-      const double devn = c->h_dev[0] < 1e-8 ? c->h_dev[0] * c->h_dev[0] : c->h_dev[1] * c->h_dev[1];
-      ok = devn < 1e-13;
-    }
-    if (ok) {
-      c->eig_fast++;
-      c->gram_levels = flev;
-      double t2 = 0.0;
-      for (size_t i = chi; i < sv.size(); ++i) t2 += sv[i] * sv[i];
-      *chi_out = chi; *trunc_out = std::sqrt(t2);
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, q, chi, p, &one, c->W, q, iso, p, &zero, absb, q));
-      dbg_tick(c, "project");
-      dbg_flush(c);
-      return BM_OK;
-    }
-    c->eig_fallback++;
-    sv.clear();
-    sigma0sq = 0.0;
-  }
   while (true) {
     ++lev;
     LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, pl, pl, q, &one, Yl, q, Yl, q, &zero, c->Gq, pl));
@@ -1069,10 +1163,10 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
     const double lmax = lam[pl - 1];
     if (lev == 1) sigma0sq = lmax;
     int kkeep = 0;
-    while (kkeep < pl && lam[pl - 1 - kkeep] > TAU * lmax) ++kkeep;
+    while (kkeep < pl && lam[pl - 1 - kkeep] > GRAM_TAU * lmax) ++kkeep;
     const int rest = pl - kkeep;
     const bool done = ((int)sv.size() + kkeep >= need) || rest == 0 || !(lmax > 0.0) ||
-                      (TAU * lmax <= cutoff * cutoff * sigma0sq) || lev >= 8;
+                      (GRAM_TAU * lmax <= cutoff * cutoff * sigma0sq) || lev >= 8;
     const int ncopy = done ? pl : kkeep;
     const double* Qtop = c->Gq + (size_t)(pl - ncopy) * pl;           // eigenvectors of the ncopy largest, ascending
     if (!T) {
@@ -1095,13 +1189,7 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
   }
   c->gram_levels = lev;
   if ((int)sv.size() > rmin) sv.resize(rmin);
-  int chi;
-  if (cutoff > 0.0) {
-    chi = 0;
-    for (double x : sv) if (x > cutoff * sv[0]) ++chi;
-    chi = std::max(chi, 1);
-    if (max_bond > 0) chi = std::min(chi, max_bond);
-  } else chi = max_bond > 0 ? std::min(max_bond, (int)sv.size()) : (int)sv.size();
+  const int chi = chi_rule(sv, cutoff, max_bond);
   double t2 = 0.0;
   for (size_t i = chi; i < sv.size(); ++i) t2 += sv[i] * sv[i];
   *chi_out = chi; *trunc_out = std::sqrt(t2);
@@ -1110,10 +1198,135 @@ static int run_svd_gram(bm_ctx* c, int mA, int nA, int going_right, int max_bond
   return BM_OK;
 }
 
-static int update_tail(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
-                       int going_right, int max_bond, double cutoff, double mom_bias,
-                       double* scalars_host, double* s_host, double sumln, double nzero);
+// The tail of a two-site step (TNutils.py:1541-1568 + write-back :1612-1617 [+ sequential_update :504-526]):
+//   A' = A - lr (A/Z - S/B + mom), renormalise, split with the quimb truncation rule, write both storage forms of the two
+//   new site tensors, optionally advance the environment cache by one site.
+// Synchronisations: one per Gram level (eigenvalues -> host) and one at the end (scalars + orthonormality checks); if
+// that last check fails the split is redone with cuSOLVER from the still intact matrix W.
+static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail_dev, double batch_total, double lr, int renorm,
+                       int going_right, int max_bond, double cutoff, double mom_bias, int advance,
+                       double* scalars_host, double* s_host) {
+  const int d = c->d;
+  const int Dl = c->sDl[k], Dr = c->sDr[k + 1];
+  const int ldr = even(Dr), ldA = d * ldr, rows = d * Dl, ncols = d * Dr;
+  const int rmin = std::min(rows, ncols);
+  const bool gram = c->svd_method == BM_SVD_GRAM || c->svd_method == BM_SVD_GRAM_SYEVD;
+  k_update<<<UPD_BLOCKS, 256, 0, c->stream>>>(c->Aint, S_dev, c->partZ, c->nZ, tail_dev, rows, ldA, Dr, ldr, batch_total, lr, mom_bias,
+                                              c->A2, c->part2, c->scal);
+  k_scale_to_colmajor<<<UPD_BLOCKS, 256, 0, c->stream>>>(c->A2, c->part2, UPD_BLOCKS, rows, ldA, d, Dr, ldr, renorm,
+                                                         (gram && going_right) ? 1 : 0, c->W, c->scal);
+  c->launches += 2;
+  KCHECK();
+  if (tail_dev) CU(cudaMemcpyAsync(c->h_scal + 8, tail_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  else c->h_scal[8] = c->h_scal[9] = 0.0;
+  CU(cudaMemcpyAsync(c->h_iscal + 3, c->tf_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int chi = 0, info = 0;
+  double trunc = 0.0;
+  bool fast = false;
+  const int p = going_right ? rows : ncols, q = going_right ? ncols : rows;
+  double* iso = going_right ? c->U : c->V;
+  double* absb = going_right ? c->V : c->U;
+  const int need = std::min(max_bond > 0 ? max_bond : rmin, rmin);
+  auto write_back = [&]() -> int {                              // gauge, both storage forms, (advance), scalars -> host
+    if (gram) {
+      c->h_iscal[0] = chi; c->h_iscal[1] = 0;
+      CU(cudaMemcpyAsync(c->iscal, c->h_iscal, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    } else {
+      k_chi<<<1, 32, 0, c->stream>>>(c->Ssv, rmin, cutoff, max_bond, c->info, c->iscal, c->scal);
+      c->launches++;
+      CU(cudaMemcpyAsync(c->h_iscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      if (s_host) CU(cudaMemcpyAsync(s_host, c->Ssv, (size_t)rmin * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaMemcpyAsync(c->h_scal, c->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    k_gauge_signs<<<32, 256, 0, c->stream>>>(c->U, rows, d, Dl, c->iscal, c->sgn);
+    k_factor_out<<<148 * 2, 256, 0, c->stream>>>(c->U, c->V, c->Ssv, c->sgn, c->iscal, d, Dl, Dr, going_right ? 1 : 0, gram ? 1 : 0,
+                                                 c->Lf(k), c->Rf(k), c->Lf(k + 1), c->Rf(k + 1));
+    c->launches += 2;
+    KCHECK();
+    return BM_OK;
+  };
+  auto set_dims = [&](int x) {
+    c->sDr[k] = x; c->sDl[k + 1] = x;
+    invalidate_site(c, k); invalidate_site(c, k + 1);
+  };
+  auto do_advance = [&]() -> int {                              // sequential_update on the new isometric site
+    if (!advance) return BM_OK;
+    if (going_right) { c->vl = k; return adv_right(c, k); }
+    c->vr = k + 2;
+    return adv_left(c, k + 1);
+  };
+  // environments the advance needs must be valid BEFORE the sites change (invalidate_site resets the bookkeeping)
+  const int vl0 = c->vl, vr0 = c->vr;
+  if (advance) {
+    if (going_right) REQUIRE(vl0 >= k, "bm_step: left environment of bond k is not valid");
+    else REQUIRE(vr0 <= k + 2, "bm_step: right environment of bond k+2 is not valid");
+  }
+  {
+    Timer t_(c, 5);
+    if (gram) {
+      if (c->svd_method == BM_SVD_GRAM && c->eig_ok && p <= EIG_NMAX && p >= 2) {
+        int r = run_svd_gram_fast(c, p, q, iso, absb, need, rmin, max_bond, cutoff, &chi, &trunc, &fast);
+        if (r != BM_OK) return r;
+      }
+      if (!fast) {
+        if (c->svd_method == BM_SVD_GRAM && c->eig_ok && p <= EIG_NMAX && p >= 2) c->eig_fallback++;
+        int r = run_svd_gram_syevd(c, p, q, iso, absb, need, rmin, max_bond, cutoff, &chi, &trunc);
+        if (r != BM_OK) return r;
+      }
+    } else {
+      int r = run_svd_gesvdj(c, rows, ncols);
+      if (r != BM_OK) return r;
+    }
+  }
+  int r = write_back();
+  if (r != BM_OK) return r;
+  if (gram) {                       // chi is known on the host: the environment advance can be enqueued before the final wait
+    set_dims(chi);
+    r = do_advance();
+    if (r != BM_OK) return r;
+  }
+  WAIT();
+  if (gram && fast) {
+    if (gram_fast_verified(c)) c->eig_fast++;
+    else {                          // rare: the eigenvectors were not orthonormal enough -> cuSOLVER levels from the intact W
+      c->eig_fallback++;
+      r = run_svd_gram_syevd(c, p, q, iso, absb, need, rmin, max_bond, cutoff, &chi, &trunc);
+      if (r != BM_OK) return r;
+      r = write_back();
+      if (r != BM_OK) return r;
+      set_dims(chi);
+      r = do_advance();
+      if (r != BM_OK) return r;
+      WAIT();
+    }
+  }
+  if (!gram) {
+    chi = c->h_iscal[0]; info = c->h_iscal[1];
+    set_dims(chi);
+    r = do_advance();
+    if (r != BM_OK) return r;
+  }
+  if (gram && s_host) std::memcpy(s_host, c->h_s.data(), std::min<size_t>(c->h_s.size(), rmin) * sizeof(double));
+  if (c->h_iscal[3] == 1) return fail(c, BM_ECUDA, "k_grad_tf32: mbarrier wait timed out (tcgen05 pipeline)");
+  if (c->h_iscal[3] == 2) return fail(c, BM_ECUDA, "k_grad_reduce_peer: a peer rank did not publish its gradient chunk (flag wait timed out)");
+  if (scalars_host) {
+    std::memcpy(scalars_host, c->h_scal, 8 * sizeof(double));
+    scalars_host[1] = c->h_scal[8]; scalars_host[2] = c->h_scal[9]; scalars_host[3] = chi;
+    if (gram) scalars_host[6] = trunc;
+  }
+  c->last_k = -1;
+  if (c->h_scal[7] > 0) return fail(c, BM_ENONFINITE, "non-finite entries in the updated merged tensor");
+  if (info != 0) return fail(c, BM_ECUSOLVER, "SVD did not converge (info=" + std::to_string(info) + ")");
+  return BM_OK;
+}
 
+static int clamp_bond(bm_ctx* c, int max_bond) {
+  if (max_bond > c->Dcap || max_bond <= 0) return c->Dcap;
+  return max_bond;
+}
+
+// scalars_host[2] > 0 (samples with psi == 0): the descent was skipped (lr = 0), the tensor was still renormalised and
+// split -- the reference's behaviour (TNutils.py:1244-1254: `crash = 0 in _psi` ... `print('RIPPERONI')`).
 int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
                    int going_right, int max_bond, double cutoff, double mom_bias,
                    double* scalars_host, double* s_host) {
@@ -1122,75 +1335,26 @@ int bm_step_update(bm_ctx* c, int k, const double* S_dev, double batch_total, do
   REQUIRE(S_dev && batch_total > 0, "bm_step_update: bad arguments");
   REQUIRE(renorm == BM_RENORM_MAX || renorm == BM_RENORM_L2, "bm_step_update: bad renorm");
   CU(cudaSetDevice(c->device));
-  const int d = c->d;
-  const int Dl = c->sDl[k], Dr = c->sDr[k + 1];
-  const int ldr = even(Dr), ldA = d * ldr, rows = d * Dl, ncols = d * Dr;
-  const int rmin = std::min(rows, ncols);
-  if (max_bond > c->Dcap || max_bond <= 0) max_bond = std::min(c->Dcap, max_bond > 0 ? max_bond : c->Dcap);
-
-  // zero-psi check before touching anything (TNutils.py:1244-1254)
-  CU(cudaMemcpyAsync(c->h_scal, S_dev + (size_t)rows * ldA, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->h_iscal + 3, c->tf_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  if (c->h_iscal[3] == 1) return fail(c, BM_ECUDA, "k_grad_tf32: mbarrier wait timed out (tcgen05 pipeline)");
-  if (c->h_iscal[3] == 2) return fail(c, BM_ECUDA, "k_grad_reduce_peer: a peer rank did not publish its gradient chunk (flag wait timed out)");
-  const double sumln = c->h_scal[0], nzero = c->h_scal[1];
-  if (nzero > 0) {
-    if (scalars_host) { std::memset(scalars_host, 0, 8 * sizeof(double)); scalars_host[1] = sumln; scalars_host[2] = nzero; }
-    return fail(c, BM_EZERO_PSI, "psi == 0 for " + std::to_string((long long)nzero) + " samples; update skipped");
-  }
-
-  return update_tail(c, k, S_dev, batch_total, lr, renorm, going_right, max_bond, cutoff, mom_bias, scalars_host, s_host, sumln, nzero);
+  const int d = c->d, Dl = c->sDl[k], Dr = c->sDr[k + 1];
+  const double* tail = S_dev + (size_t)d * Dl * d * even(Dr);
+  return update_tail(c, k, S_dev, tail, batch_total, lr, renorm, going_right, clamp_bond(c, max_bond), cutoff, mom_bias, 0,
+                     scalars_host, s_host);
 }
 
-static int update_tail(bm_ctx* c, int k, const double* S_dev, double batch_total, double lr, int renorm,
-                       int going_right, int max_bond, double cutoff, double mom_bias,
-                       double* scalars_host, double* s_host, double sumln, double nzero) {
-  const int d = c->d;
-  const int Dl = c->sDl[k], Dr = c->sDr[k + 1];
-  const int ldr = even(Dr), ldA = d * ldr, rows = d * Dl, ncols = d * Dr;
-  const int rmin = std::min(rows, ncols);
-  const bool gram = c->svd_method == BM_SVD_GRAM || c->svd_method == BM_SVD_GRAM_SYEVD;
-  k_update<<<RED_BLOCKS, 256, 0, c->stream>>>(c->Aint, S_dev, c->partZ, rows, ldA, Dr, ldr, batch_total, lr, mom_bias, c->A2, c->part2, c->scal);
-  k_scale_to_colmajor<<<RED_BLOCKS * 4, 256, 0, c->stream>>>(c->A2, c->part2, rows, ldA, d, Dr, ldr, renorm,
-                                                             (gram && going_right) ? 1 : 0, c->W, c->scal);
-  c->launches += 2;
-  KCHECK();
-  int chi = 0, info = 0;
-  double trunc = 0.0;
-  if (gram) {
-    int r = run_svd_gram(c, rows, ncols, going_right ? 1 : 0, max_bond, cutoff, &chi, &trunc);
-    if (r != BM_OK) return r;
-    c->h_iscal[0] = chi; c->h_iscal[1] = 0;
-    CU(cudaMemcpyAsync(c->iscal, c->h_iscal, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    if (s_host) std::memcpy(s_host, c->h_s.data(), std::min<size_t>(c->h_s.size(), rmin) * sizeof(double));
-  } else {
-    int r = run_svd_gesvdj(c, rows, ncols);
-    if (r != BM_OK) return r;
-    k_chi<<<1, 32, 0, c->stream>>>(c->Ssv, rmin, cutoff, max_bond, c->info, c->iscal, c->scal);
-    c->launches++;
-    CU(cudaMemcpyAsync(c->h_iscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (s_host) CU(cudaMemcpyAsync(s_host, c->Ssv, (size_t)rmin * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  }
-  CU(cudaMemcpyAsync(c->h_scal, c->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  k_gauge_signs<<<32, 256, 0, c->stream>>>(c->U, rows, d, Dl, c->iscal, c->sgn);
-  k_factor_out<<<148 * 2, 256, 0, c->stream>>>(c->U, c->V, c->Ssv, c->sgn, c->iscal, d, Dl, Dr, going_right ? 1 : 0, gram ? 1 : 0,
-                                               c->Lf(k), c->Rf(k), c->Lf(k + 1), c->Rf(k + 1));
-  c->launches += 2;
-  KCHECK();
-  CU(cudaStreamSynchronize(c->stream));
-  if (!gram) { chi = c->h_iscal[0]; info = c->h_iscal[1]; }
-  if (scalars_host) {
-    std::memcpy(scalars_host, c->h_scal, 8 * sizeof(double));
-    scalars_host[1] = sumln; scalars_host[2] = nzero; scalars_host[3] = chi;
-    if (gram) scalars_host[6] = trunc;
-  }
-  c->sDr[k] = chi; c->sDl[k + 1] = chi;
-  invalidate_site(c, k); invalidate_site(c, k + 1);
-  c->last_k = -1;
-  if (c->h_scal[7] > 0) return fail(c, BM_ENONFINITE, "non-finite entries in the updated merged tensor");
-  if (info != 0) return fail(c, BM_ECUSOLVER, "SVD did not converge (info=" + std::to_string(info) + ")");
-  return BM_OK;
+// One whole two-site step in ONE call (learning_step_cached + write-back + sequential_update, TNutils.py:1603-1620):
+// bm_step_grad + bm_step_update + bm_env_advance without returning to the caller in between.  With several ranks this
+// needs the fused peer all-reduce (bm_peer_import); the NCCL path has to go through bm_step_grad / bm_step_update.
+int bm_step(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double* S_dev, double batch_total, double lr, int renorm,
+            int going_right, int max_bond, double cutoff, double mom_bias, int advance, double* scalars_host, double* s_host) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(batch_total > 0, "bm_step: bad batch_total");
+  REQUIRE(renorm == BM_RENORM_MAX || renorm == BM_RENORM_L2, "bm_step: bad renorm");
+  int r = bm_step_grad(c, k, mask_host, n_mask, S_dev);
+  if (r != BM_OK) return r;
+  const int d = c->d, Dl = c->sDl[k], Dr = c->sDr[k + 1];
+  const double* tail = S_dev + (size_t)d * Dl * d * even(Dr);
+  return update_tail(c, k, S_dev, tail, batch_total, lr, renorm, going_right, clamp_bond(c, max_bond), cutoff, mom_bias, advance ? 1 : 0,
+                     scalars_host, s_host);
 }
 
 // merge + split only (no gradient step, no renormalisation): compress / canonicalisation sweeps
@@ -1205,9 +1369,9 @@ int bm_split_bond(bm_ctx* c, int k, int going_right, int max_bond, double cutoff
   const int d = c->d, Dl = c->sDl[k], Dr = c->sDr[k + 1];
   const size_t cnt = (size_t)d * Dl * d * even(Dr);
   CU(cudaMemsetAsync(c->G, 0, cnt * sizeof(double), c->stream));
-  if (max_bond > c->Dcap || max_bond <= 0) max_bond = c->Dcap;
   c->last_k = k;
-  return update_tail(c, k, c->G, 1.0, 0.0, 2 /* no renormalisation */, going_right, max_bond, cutoff, 0.0, scalars_host, s_host, 0.0, 0.0);
+  return update_tail(c, k, c->G, nullptr, 1.0, 0.0, 2 /* no renormalisation */, going_right, clamp_bond(c, max_bond), cutoff, 0.0, 0,
+                     scalars_host, s_host);
 }
 
 int bm_get_merged(bm_ctx* c, double* A_host) {
@@ -1434,7 +1598,6 @@ int bm_peer_export(bm_ctx* c, void* handle64_out) {
   if (!c->peer_buf) {
     DALLOC(c->peer_buf, 2 * c->peer_slot_elems + flag_doubles);
     CU(cudaMemset(c->peer_buf, 0, (2 * c->peer_slot_elems + flag_doubles) * sizeof(double)));
-    DALLOC(c->tail_local, 2);
   }
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, c->peer_buf));

@@ -106,6 +106,7 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity)
 // double-buffered by the parity of j.
 constexpr int SYTRD_MSG = 2 * EIG_LR + 2;                     // p[32], column slice[32], p.v, pad -> 528 bytes
 constexpr uint32_t SYTRD_TX_BYTES = EIG_CL * SYTRD_MSG * 8;
+template <bool ONE_POLLER>
 __global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_NT, 1)
 k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict__ d, double* __restrict__ e,
                 double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status) {
@@ -227,7 +228,14 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       V[(size_t)j * EIG_LDV + t] = vt;
       if (t == 0) { e[j] = beta; tau[j] = tj; }
     }
-    ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
+    // ONE_POLLER: only warp 0 polls the mbarrier, the other warps sleep at the hardware CTA barrier (15 polling warps
+    // congest the shared-memory/shuffle queue that warp 0's send path needs: ncu + phase clocks, r02_sytrd_phases.log)
+    if (ONE_POLLER) {
+      if (warp == 0) ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
+      __syncthreads();
+    } else {
+      ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
+    }
     // ---- D: w, the next full column, rank-2 update of my block
     double dsum[EIG_CL];
 #pragma unroll
@@ -273,6 +281,251 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (n >= 2 && r == n - 1 && 4 * cg + k == n - 1) d[n - 1] = a[i][k];
+  }
+  if (!ok && t == 0) atomicExch(status, 3);
+  cluster_sync_all();                             // nobody exits while a peer could still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_sytrd_fused — second generation of the tridiagonalisation: same arithmetic, outputs, distribution over the 16-CTA
+// cluster and exchange mechanism (one bulk copy per destination, mbarrier transaction count) as k_sytrd_cluster, with
+// the per-column critical path restructured around what ncu showed (profiles/r01_ncu_eig_kernels.md):
+//  * thread layout 2 rows x 16 columns (warp w: local rows 2w, 2w+1; lane l: columns 2l+64i, 2l+64i+1): a row's inner
+//    product lives in ONE warp (5 shuffle rounds, the first one transposing the two rows onto the two half-warps), no
+//    cross-warp partial sums;
+//  * the rank-2 update of column j-1 and the product with column j are ONE pass over the registers;
+//  * the squared norm of column j+1 is reduced while that column is formed and the Householder scalars are computed
+//    redundantly by every thread off the critical path: two CTA barriers per column instead of four.
+// A flag-in-data ("LL") exchange with per-warp remote stores was measured and rejected: the SM-to-SM network costs
+// ~3.5 cycles per 16-byte packet, 4600 cycles per round (tools/probe/probe_ll.cu, profiles/r02_probe_ll.json).
+// ------------------------------------------------------------------------------------------------------------------
+struct SytrdFusedSmem {
+  double rbuf[2][EIG_CL][SYTRD_MSG];  // received messages, one per source CTA: p[32], column slice[32], p.v, pad
+  double sbuf[2][SYTRD_MSG];          // my outgoing message
+  double xh[2][EIG_NMAX];             // masked current column (zero for rows <= j)
+  double vf[2][EIG_NMAX];             // Householder vector of column j
+  double wf[2][EIG_NMAX];             // w of column j
+  double nrm[2][16];                  // per-warp partial squared norms of the next column
+  double dpart[16];                   // per-warp partial p.v
+  unsigned long long bars[2];
+};
+
+__global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_NT, 1)
+k_sytrd_fused(const double* __restrict__ G, int ld, int n, double* __restrict__ d, double* __restrict__ e,
+              double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status, long long* __restrict__ prof) {
+  extern __shared__ __align__(16) unsigned char sytrd_raw[];
+  SytrdFusedSmem& S = *reinterpret_cast<SytrdFusedSmem*>(sytrd_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int me = (int)cluster_ctarank();
+  const int half = lane >> 4;
+  const int row0 = me + 2 * EIG_CL * warp, row1 = row0 + EIG_CL;   // global rows of this warp
+  const int myrow = half ? row1 : row0;                            // the row this lane reports after the reduction
+  const int mylr = 2 * warp + half;                                // its local index (0..31)
+  double a[2][8][2];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = rr ? row1 : row0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = 64 * i + 2 * lane;
+      a[rr][i][0] = (r < n && c < n) ? G[(size_t)r * ld + c] : 0.0;          // G is symmetric
+      a[rr][i][1] = (r < n && c + 1 < n) ? G[(size_t)r * ld + c + 1] : 0.0;
+    }
+  }
+  double x = t < n ? G[t] : 0.0;                                    // full column 0 (one entry per thread)
+  S.xh[0][t] = t > 0 ? x : 0.0;
+  {
+    const double s = warp_sum(t > 1 ? x * x : 0.0);
+    if (lane == 0) S.nrm[0][warp] = s;
+  }
+  if (t == 0) {
+    mbar_init(eig_smem_u32(&S.bars[0]), 1);
+    mbar_init(eig_smem_u32(&S.bars[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                             // every CTA resident, barriers initialised
+  bool ok = true;
+  // optional phase clocks (prof != nullptr): lane 0 of warps 0 and 15 of CTA 0 accumulate the cycles between the marks
+  const bool pr = prof != nullptr && me == 0 && lane == 0 && (warp == 0 || warp == 15);
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0, sub[3] = {0, 0, 0};
+#define SY_MARK(i) do { if (pr) { const long long now_ = clock64(); ph[i] += now_ - tc; tc = now_; } } while (0)
+  if (pr) tc = clock64();
+  for (int j = 0; j + 2 < n; ++j) {
+    const int par = j & 1;
+    const double* __restrict__ xhp = S.xh[par];
+    const double* __restrict__ pv = S.vf[par ^ 1];
+    const double* __restrict__ pw = S.wf[par ^ 1];
+    const double alpha = xhp[j + 1];
+    // ---- one pass over the registers: rank-2 update of column j-1, then q = A xh on my two rows
+    double q0[4] = {0.0, 0.0, 0.0, 0.0}, q1[4] = {0.0, 0.0, 0.0, 0.0};
+    if (row1 > j) {                                // warp-uniform: both rows finished -> nothing to do
+      const bool live0 = row0 > j, upd = j > 0;
+      const double nv0 = -pv[row0], nw0 = -pw[row0], nv1 = -pv[row1], nw1 = -pw[row1];
+      const int ib0 = (j + 1) >> 6;               // column blocks below ib0 are finished for every lane
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < ib0) continue;
+        const int c = 64 * i + 2 * lane;
+        const double2 xx = *reinterpret_cast<const double2*>(&xhp[c]);
+        if (upd) {
+          const double2 vv = *reinterpret_cast<const double2*>(&pv[c]);
+          const double2 ww = *reinterpret_cast<const double2*>(&pw[c]);
+          a[1][i][0] = fma(nv1, ww.x, fma(nw1, vv.x, a[1][i][0]));
+          a[1][i][1] = fma(nv1, ww.y, fma(nw1, vv.y, a[1][i][1]));
+          if (live0) {
+            a[0][i][0] = fma(nv0, ww.x, fma(nw0, vv.x, a[0][i][0]));
+            a[0][i][1] = fma(nv0, ww.y, fma(nw0, vv.y, a[0][i][1]));
+          }
+        }
+        q1[2 * (i & 1)] = fma(a[1][i][0], xx.x, q1[2 * (i & 1)]);
+        q1[2 * (i & 1) + 1] = fma(a[1][i][1], xx.y, q1[2 * (i & 1) + 1]);
+        if (live0) {
+          q0[2 * (i & 1)] = fma(a[0][i][0], xx.x, q0[2 * (i & 1)]);
+          q0[2 * (i & 1) + 1] = fma(a[0][i][1], xx.y, q0[2 * (i & 1) + 1]);
+        }
+      }
+    }
+    SY_MARK(0);                                    // fused pass
+    // ---- my rows' entries of column j+1 (after update j-1): held by lane ((j+1) & 63) >> 1
+    double sl0 = 0.0, sl1 = 0.0;
+    {
+      const int cj = j + 1, kb = cj & 1;
+      switch (cj >> 6) {                           // block-uniform
+        case 0: sl0 = kb ? a[0][0][1] : a[0][0][0]; sl1 = kb ? a[1][0][1] : a[1][0][0]; break;
+        case 1: sl0 = kb ? a[0][1][1] : a[0][1][0]; sl1 = kb ? a[1][1][1] : a[1][1][0]; break;
+        case 2: sl0 = kb ? a[0][2][1] : a[0][2][0]; sl1 = kb ? a[1][2][1] : a[1][2][0]; break;
+        case 3: sl0 = kb ? a[0][3][1] : a[0][3][0]; sl1 = kb ? a[1][3][1] : a[1][3][0]; break;
+        case 4: sl0 = kb ? a[0][4][1] : a[0][4][0]; sl1 = kb ? a[1][4][1] : a[1][4][0]; break;
+        case 5: sl0 = kb ? a[0][5][1] : a[0][5][0]; sl1 = kb ? a[1][5][1] : a[1][5][0]; break;
+        case 6: sl0 = kb ? a[0][6][1] : a[0][6][0]; sl1 = kb ? a[1][6][1] : a[1][6][0]; break;
+        default: sl0 = kb ? a[0][7][1] : a[0][7][0]; sl1 = kb ? a[1][7][1] : a[1][7][0]; break;
+      }
+      const int src = (cj & 63) >> 1;
+      sl0 = __shfl_sync(0xffffffffu, sl0, src);
+      sl1 = __shfl_sync(0xffffffffu, sl1, src);
+    }
+    const double slice = half ? sl1 : sl0;
+    // ---- Householder scalars (every thread, bit-identical everywhere) -- independent of the reduction below
+    double beta = alpha, tj = 0.0, scale = 0.0;
+    {
+      double nr[8];                                // partial norms of column j: fixed tree, identical in every thread
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double2 v2 = *reinterpret_cast<const double2*>(&S.nrm[par][2 * k]);
+        nr[k] = v2.x + v2.y;
+      }
+#pragma unroll
+      for (int w = 4; w > 0; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) nr[k] += nr[k + w];
+      const double xn2 = nr[0];
+      if (xn2 != 0.0) {
+        const double nn = fma(alpha, alpha, xn2);
+        const double rinv = fast_rsqrt(nn);                     // 1/|beta|
+        beta = -copysign(nn * rinv, alpha);
+        tj = (beta - alpha) * (-copysign(rinv, alpha));          // (beta - alpha) / beta
+        scale = fast_rcp(alpha - beta);
+      }
+    }
+    const double vt = (t > j + 1) ? x * scale : (t == j + 1 ? 1.0 : 0.0);
+    S.vf[par][t] = vt;
+    SY_MARK(1);                                    // slice broadcast + Householder scalars
+    // ---- row sums: the first round moves row 0 onto lanes 0-15 and row 1 onto lanes 16-31
+    double qs;
+    {
+      const double s0 = (q0[0] + q0[1]) + (q0[2] + q0[3]), s1 = (q1[0] + q1[1]) + (q1[2] + q1[3]);
+      const double send = half ? s0 : s1, keep = half ? s1 : s0;
+      qs = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+    }
+    {
+      const double p = (myrow > j && myrow < n) ? (tj * scale) * fma(-beta, slice, qs) : 0.0;
+      const double vr = (myrow > j + 1) ? xhp[myrow] * scale : (myrow == j + 1 ? 1.0 : 0.0);
+      double dp = p * vr;
+      dp += __shfl_xor_sync(0xffffffffu, dp, 16);
+      if ((lane & 15) == 0) {
+        S.sbuf[par][mylr] = p;
+        S.sbuf[par][EIG_LR + mylr] = slice;
+        if (lane == 0) S.dpart[warp] = dp;
+        fence_proxy_async_smem();                  // my generic-proxy writes precede the bulk copies issued after the barrier
+      }
+    }
+    if (me == (j & (EIG_CL - 1))) {
+      V[(size_t)j * EIG_LDV + t] = vt;
+      if (t == 0) { e[j] = beta; tau[j] = tj; }
+    }
+    if (me == 0 && t == j) d[j] = x;
+    SY_MARK(2);                                    // row sums, p, partial dot, message
+    __syncthreads();                               // message complete
+    SY_MARK(3);                                    // barrier
+    if (warp == 0) {
+      double dsum = lane < 16 ? S.dpart[lane] : 0.0;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+      if (pr) { const long long now_ = clock64(); sub[0] += now_ - tc; }
+      if (lane == 0) {
+        S.sbuf[par][2 * EIG_LR] = dsum;
+        fence_proxy_async_smem();
+        if (pr) { const long long now_ = clock64(); sub[1] += now_ - tc; }
+        mbar_expect_tx(eig_smem_u32(&S.bars[par]), SYTRD_TX_BYTES);
+      }
+      __syncwarp();
+      if (pr) { const long long now_ = clock64(); sub[2] += now_ - tc; }
+      if (lane < EIG_CL)
+        bulk_copy_to_cta(mapa_u32(eig_smem_u32(&S.rbuf[par][me][0]), lane), eig_smem_u32(&S.sbuf[par][0]), SYTRD_MSG * 8,
+                         mapa_u32(eig_smem_u32(&S.bars[par]), lane));
+    }
+    SY_MARK(4);                                    // (warp 0) dot sum + bulk copies issued
+    ok = mbar_wait_cluster(eig_smem_u32(&S.bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
+    SY_MARK(5);                                    // exchange wait
+    // ---- w, the next full column and its partial norms
+    double dsum[EIG_CL / 2];
+#pragma unroll
+    for (int c = 0; c < EIG_CL / 2; ++c) dsum[c] = S.rbuf[par][2 * c][2 * EIG_LR] + S.rbuf[par][2 * c + 1][2 * EIG_LR];
+#pragma unroll
+    for (int w = EIG_CL / 4; w > 0; w >>= 1)
+#pragma unroll
+      for (int c = 0; c < w; ++c) dsum[c] += dsum[c + w];       // fixed tree: identical in every thread of every CTA
+    const double al2 = -0.5 * tj * dsum[0];
+    const double wt = fma(al2, vt, S.rbuf[par][t & 15][t >> 4]);
+    const double wj1 = S.rbuf[par][(j + 1) & 15][(j + 1) >> 4] + al2;   // v[j+1] = 1
+    const double xnew = S.rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);      // column j+1 of A - v w^T - w v^T
+    S.wf[par][t] = wt;
+    S.xh[par ^ 1][t] = (t > j + 1) ? xnew : 0.0;
+    {
+      const double s = warp_sum(t > j + 2 ? xnew * xnew : 0.0);
+      if (lane == 0) S.nrm[par ^ 1][warp] = s;
+    }
+    x = xnew;
+    SY_MARK(6);                                    // w, next column, partial norms
+    __syncthreads();
+    SY_MARK(7);                                    // barrier
+  }
+  if (pr) for (int i = 0; i < 8; ++i) prof[(warp == 0 ? 0 : 8) + i] = ph[i];
+  if (pr && warp == 0) for (int i = 0; i < 3; ++i) prof[16 + i] = sub[i];
+#undef SY_MARK
+  // ---- trailing 2 x 2 block: x is column n-2 (n >= 2) or column 0; element (n-1, n-1) still lacks update n-3
+  if (me == 0) {
+    if (n >= 2) {
+      if (t == n - 2) d[n - 2] = x;
+      if (t == n - 1) e[n - 2] = x;
+    } else if (t == 0) d[0] = x;
+  }
+  if (n >= 2) {
+    const int last = n - 3;                                     // pending update (none if n == 2)
+    double corr = 0.0;
+    if (last >= 0) corr = -2.0 * S.vf[last & 1][n - 1] * S.wf[last & 1][n - 1];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = rr ? row1 : row0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (r == n - 1 && 64 * i + 2 * lane + k == n - 1) d[n - 1] = a[rr][i][k] + corr;
+    }
   }
   if (!ok && t == 0) atomicExch(status, 3);
   cluster_sync_all();                             // nobody exits while a peer could still address its shared memory
@@ -474,6 +727,146 @@ __global__ void __launch_bounds__(32) k_tri_vectors(const double* __restrict__ d
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// k_tri_vectors3 — the same twisted factorisation with the pivots taken from the three-term recurrence
+//   p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2},   D+_i = p_i / p_{i-1},   L+_{i-1} = e_{i-1} p_{i-2} / p_{i-1}
+// (and its mirror image from the bottom), so that the reciprocal leaves the dependency chain: one dependent FMA per row
+// instead of reciprocal + multiply + FMA (k_tri_vectors: 170 cycles per row).  Rows are processed in groups of 8 without
+// zero checks on the chain; a group that produced an exact zero is redone with the careful rule (zero -> tiny).  The
+// pair (p_i, p_{i-1}) is rescaled by a power of two per group; T is normalised to |entries| <= 1 first.
+// Numerics: tools/eigfast_proto.py --three-term (same orthogonality and residuals as the qd form).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_tri_vectors3(const double* __restrict__ d, const double* __restrict__ e, int n,
+                                                     const double* __restrict__ lam, int m,
+                                                     double* __restrict__ Zt, double* __restrict__ znorm) {
+  extern __shared__ __align__(16) double tv_smem[];
+  double* sd = tv_smem;                                    // [n]
+  double* se = sd + EIG_NMAX;                              // [n]
+  double* sDp = se + EIG_NMAX;                             // [n][8]
+  double* sLp = sDp + EIG_NMAX * TV_EIG;
+  double* sDm = sLp + EIG_NMAX * TV_EIG;
+  double* sUm = sDm + EIG_NMAX * TV_EIG;
+  __shared__ double gbest[2][TV_EIG];
+  __shared__ int ibest[2][TV_EIG];
+  __shared__ double ssq[2][TV_EIG];
+  const int lane = threadIdx.x, dir = (lane >> 3) & 1, q = lane & 7;
+  double tn = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const double di = d[i], ei = i + 1 < n ? e[i] : 0.0;
+    sd[i] = di; se[i] = ei;
+    tn = fmax(tn, fmax(fabs(di), fabs(ei)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tn = fmax(tn, __shfl_xor_sync(0xffffffffu, tn, o));
+  int ex = ((__double2hiint(tn) >> 20) & 0x7ff) - 1023 + 2;     // |d_i - x| + e^2 <= 1 after scaling
+  if (!(tn > 0.0) || ex < -900 || ex > 900) ex = 0;
+  const double sdown = __hiloint2double((1023 - ex) << 20, 0);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) { sd[i] *= sdown; se[i] *= sdown; }
+  __syncwarp();
+  const int c = blockIdx.x * TV_EIG + q;
+  const bool act = lane < 16 && c < m;
+  const double x = act ? lam[n - 1 - c] * sdown : 0.0;
+  constexpr double TINY = 1.1754943508222875e-271;           // 2^-900
+  if (act) {
+    double* Dout = dir ? sDm : sDp;
+    double* Lout = dir ? sUm : sLp;
+    // step i handles row r_i = dir ? n-1-i : i; its coupling to the previous row is e[dir ? n-1-i : i-1]
+    double pp = 1.0, p = (dir ? sd[n - 1] : sd[0]) - x;
+    if (p == 0.0) p = TINY;
+    Dout[(dir ? n - 1 : 0) * TV_EIG + q] = p;
+    int i = 1;
+    for (; i + 8 <= n; i += 8) {
+      double dxv[8], ev[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = dir ? n - 1 - (i + u) : i + u;
+        dxv[u] = sd[r] - x;
+        ev[u] = se[dir ? r : r - 1];
+      }
+      double Dv[8], Lv[8];
+      double fp = p, fpp = pp;
+      bool zero = false;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double rinv = fast_rcp(fp);
+        Lv[u] = ev[u] * fpp * rinv;
+        const double pn = fma(dxv[u], fp, -(ev[u] * ev[u]) * fpp);
+        Dv[u] = pn * rinv;
+        zero = zero || pn == 0.0;
+        fpp = fp; fp = pn;
+      }
+      if (zero) {                                              // careful pass: an exact zero becomes a tiny pivot
+        fp = p; fpp = pp;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double rinv = fast_rcp(fp);
+          Lv[u] = ev[u] * fpp * rinv;
+          double pn = fma(dxv[u], fp, -(ev[u] * ev[u]) * fpp);
+          if (pn == 0.0) pn = fp * TINY;
+          Dv[u] = pn * rinv;
+          fpp = fp; fp = pn;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = dir ? n - 1 - (i + u) : i + u;
+        Dout[r * TV_EIG + q] = Dv[u];
+        Lout[(dir ? r : r - 1) * TV_EIG + q] = Lv[u];
+      }
+      p = fp; pp = fpp;
+      const int hi = __double2hiint(fmax(fabs(p), fabs(pp)));
+      const int pe = ((hi >> 20) & 0x7ff) - 1023;
+      if (pe > 64 || pe < -64) {
+        const double sc = __hiloint2double((1023 - max(-960, min(960, pe))) << 20, 0);
+        p *= sc; pp *= sc;
+      }
+    }
+    for (; i < n; ++i) {
+      const int r = dir ? n - 1 - i : i;
+      const double ev = se[dir ? r : r - 1];
+      const double rinv = fast_rcp(p);
+      Lout[(dir ? r : r - 1) * TV_EIG + q] = ev * pp * rinv;
+      double pn = fma(sd[r] - x, p, -(ev * ev) * pp);
+      if (pn == 0.0) pn = p * TINY;
+      Dout[r * TV_EIG + q] = pn * rinv;
+      pp = p; p = pn;
+    }
+  }
+  __syncwarp();
+  const int mid = n / 2;
+  if (act) {
+    double gb = DBL_MAX; int ib = dir == 0 ? 0 : mid;
+    const int i0 = dir == 0 ? 0 : mid, i1 = dir == 0 ? mid : n;
+    for (int i = i0; i < i1; ++i) {
+      const double gm = fabs(sDp[i * TV_EIG + q] + sDm[i * TV_EIG + q] - (sd[i] - x));
+      if (gm < gb) { gb = gm; ib = i; }          // NaN never wins
+    }
+    gbest[dir][q] = gb; ibest[dir][q] = ib;
+  }
+  __syncwarp();
+  if (act) {
+    const size_t cs = (size_t)m;
+    const int r = (gbest[1][q] < gbest[0][q]) ? ibest[1][q] : ibest[0][q];
+    double s2 = 0.0, z = 1.0;
+    if (dir == 0) {
+      Zt[r * cs + c] = 1.0; s2 = 1.0;
+      for (int i = r - 1; i >= 0; --i) {
+        z = -sLp[i * TV_EIG + q] * z;
+        Zt[i * cs + c] = z; s2 = fma(z, z, s2);
+      }
+    } else {
+      for (int i = r; i + 1 < n; ++i) {
+        z = -sUm[i * TV_EIG + q] * z;
+        Zt[(size_t)(i + 1) * cs + c] = z; s2 = fma(z, z, s2);
+      }
+    }
+    ssq[dir][q] = s2;
+  }
+  __syncwarp();
+  if (act && dir == 0) znorm[c] = rsqrt(ssq[0][q] + ssq[1][q]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // back-transformation  U[:, c] = H_0 H_1 ... H_{n-3} z_c / |z_c| : one warp per eigenvector, 16 rows per lane in
 // registers, reflectors streamed from L2 (v_j is zero on rows <= j; row blocks above the support are skipped).
 // ------------------------------------------------------------------------------------------------------------------
@@ -616,23 +1009,18 @@ __global__ void __launch_bounds__(REFL_WARPS * 32) k_apply_reflectors(const doub
   }
 }
 
-// C (mp x mp, ld) holds U^T U, of which the leading m x m block belongs to real columns (the rest is zero padding that
-// keeps the cuBLAS shapes on multiples of 64).  dev[0] = max(dev[0], max |C - I| over the real block) -- zero it
-// before the launch; C <- 1.5 I - 0.5 C, the
-// Newton-Schulz factor:  U <- U C  squares the deviation from orthonormality (zero columns stay zero).
-constexpr int POLISH_BLOCKS = 64;
-__global__ void __launch_bounds__(256) k_polish_coef(double* __restrict__ C, int mp, int ld, int m, double* __restrict__ dev) {
+// C (m x m, ld) holds U^T U.  dev[0] = max(dev[0], max |C - I|) -- zero it before the launch;  C <- 1.5 I - 0.5 C, the
+// Newton-Schulz factor:  U <- U C  squares the deviation from orthonormality.
+constexpr int POLISH_BLOCKS = 128;
+__global__ void __launch_bounds__(256) k_polish_coef(double* __restrict__ C, int m, int ld, double* __restrict__ dev) {
   __shared__ double red[8];
   double mx = 0.0;
-  // one column per step of the block loop: no integer division
-  for (int j = blockIdx.x; j < mp; j += gridDim.x) {
+  for (int j = blockIdx.x; j < m; j += gridDim.x) {         // one column per step of the block loop: no integer division
     double* col = C + (size_t)j * ld;
-    for (int i = threadIdx.x; i < mp; i += 256) {
+    for (int i = threadIdx.x; i < m; i += 256) {
       const double x = col[i];
-      if (i < m && j < m) {
-        const double dv = fabs(x - (i == j ? 1.0 : 0.0));
-        if (!(dv <= mx)) mx = (dv == dv) ? dv : DBL_MAX;    // NaN -> reported as a huge deviation
-      }
+      const double dv = fabs(x - (i == j ? 1.0 : 0.0));
+      if (!(dv <= mx)) mx = (dv == dv) ? dv : DBL_MAX;      // NaN -> reported as a huge deviation
       col[i] = (i == j ? 1.5 : 0.0) - 0.5 * x;
     }
   }

@@ -77,6 +77,51 @@ __device__ __forceinline__ double pow2d(int e) {   // exact 2^e, e in [-1022,102
   return __longlong_as_double((long long)(e + 1023) << 52);
 }
 
+// ---- block-level reductions (fixed order: deterministic) ----------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  __syncthreads();
+  return r;   // valid in thread 0
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = -INFINITY;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmax(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+
+// deterministic block-wide sum / max of part[0], part[stride], ... (count values), valid in every thread
+__device__ __forceinline__ double block_total(const double* __restrict__ part, int count, int stride, double* sh /* [9] */) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s += part[(long long)i * stride];
+  const double r = block_sum(s, sh);
+  if (threadIdx.x == 0) sh[8] = r;
+  __syncthreads();
+  const double out = sh[8];
+  __syncthreads();
+  return out;
+}
+__device__ __forceinline__ double block_total_max(const double* __restrict__ part, int count, int stride, double* sh /* [9] */) {
+  double s = -INFINITY;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s = fmax(s, part[(long long)i * stride]);
+  const double r = block_max(s, sh);
+  if (threadIdx.x == 0) sh[8] = r;
+  __syncthreads();
+  const double out = sh[8];
+  __syncthreads();
+  return out;
+}
+
+
 // Row grouping: rows [goff[g], goff[g+1]) of `perm` share matrix  B + (g / gdiv) * strideHi + (g % gdiv) * strideLo.
 struct GroupSpec {
   const int* perm;     // sample ids, grouped (nullptr = identity)
@@ -350,10 +395,12 @@ struct PsiParams {
   GroupSpec gs;
   const int* cumeL; const int* cumeR;
   double* psi; double* winv; double* lnpsi;
+  double* part;            // [2 * gridDim.x]: per-CTA sum of ln|psi| over psi != 0, number of psi == 0 (fixed order)
 };
 
 template <int TM>
-__device__ __forceinline__ void tile_psi(const PsiParams& P, unsigned char* smem_raw, int g, int row0, int nrows) {
+__device__ __forceinline__ void tile_psi(const PsiParams& P, unsigned char* smem_raw, int g, int row0, int nrows,
+                                         double& acc_ln, double& acc_zero) {
   constexpr int MT = TM / 16;
   PanelSmem<TM>& sm = *reinterpret_cast<PanelSmem<TM>*>(smem_raw);
   __shared__ const double* rowptr[TM];
@@ -429,17 +476,33 @@ __device__ __forceinline__ void tile_psi(const PsiParams& P, unsigned char* smem
     double psi = (rsum[tid][0] + rsum[tid][1]) + (rsum[tid][2] + rsum[tid][3]);
     P.psi[id] = psi;
     P.winv[id] = psi != 0.0 ? 1.0 / psi : 0.0;
-    P.lnpsi[id] = log(fabs(psi)) + (double)(P.cumeL[id] + P.cumeR[id]) * LN2;
+    const double ln = log(fabs(psi)) + (double)(P.cumeL[id] + P.cumeR[id]) * LN2;
+    P.lnpsi[id] = ln;
+    if (psi == 0.0) acc_zero += 1.0; else acc_ln += ln;
   }
 }
 
 __global__ void __launch_bounds__(NTHREADS, BM_MINBLOCKS) k_psi(PsiParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  double acc_ln = 0.0, acc_zero = 0.0;       // rows finished by this thread (tid < tile height), in tile order
   for_each_tile(P.gs.goff, P.gs.ngroups, [&](int tm, int g, int row0, int nrows) {
-    if (tm == 64) tile_psi<64>(P, smem_raw, g, row0, nrows);
-    else if (tm == 32) tile_psi<32>(P, smem_raw, g, row0, nrows);
-    else tile_psi<16>(P, smem_raw, g, row0, nrows);
+    if (tm == 64) tile_psi<64>(P, smem_raw, g, row0, nrows, acc_ln, acc_zero);
+    else if (tm == 32) tile_psi<32>(P, smem_raw, g, row0, nrows, acc_ln, acc_zero);
+    else tile_psi<16>(P, smem_raw, g, row0, nrows, acc_ln, acc_zero);
   });
+  if (P.part) {                              // fixed assignment of rows to CTAs and threads + fixed-order sums: deterministic
+    __shared__ double psi_sh[2][NTHREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) { acc_ln += __shfl_xor_sync(0xffffffffu, acc_ln, o); acc_zero += __shfl_xor_sync(0xffffffffu, acc_zero, o); }
+    __syncthreads();
+    if (lane == 0) { psi_sh[0][w] = acc_ln; psi_sh[1][w] = acc_zero; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double r = 0.0;
+      for (int i = 0; i < NTHREADS / 32; ++i) r += psi_sh[threadIdx.x][i];
+      P.part[2 * blockIdx.x + threadIdx.x] = r;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -733,8 +796,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_grad_tf32(GradParams P, int* 
 }
 
 // S[e] = sum over the splits of e's group, in split order (deterministic).  Pads are written as 0.
-__global__ void k_grad_reduce(const double* __restrict__ ws, long long ws_stride, const int* __restrict__ goff,
-                              int kchunk, int d, int Dl, int Dr, int ldA, int ldRpad, double* __restrict__ S) {
+__global__ void __launch_bounds__(256) k_grad_reduce(const double* __restrict__ ws, long long ws_stride, const int* __restrict__ goff,
+                                                     int kchunk, int d, int Dl, int Dr, int ldA, int ldRpad, double* __restrict__ S,
+                                                     const double* __restrict__ psi_part, int npart) {
   const long long total = (long long)d * Dl * ldA;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int row = (int)(e / ldA), col = (int)(e % ldA);
@@ -747,6 +811,11 @@ __global__ void k_grad_reduce(const double* __restrict__ ws, long long ws_stride
       for (int i = 0; i < ns; ++i) s += ws[(long long)i * ws_stride + e];
     }
     S[e] = s;
+  }
+  if (psi_part && blockIdx.x == gridDim.x - 1) {      // tail: [sum ln|psi|, #(psi == 0)] from the per-CTA partials of k_psi
+    __shared__ double sh[9];
+    const double sl = block_total(psi_part, npart, 2, sh), sz = block_total(psi_part + 1, npart, 2, sh);
+    if (threadIdx.x == 0) { S[total] = sl; S[total + 1] = sz; }
   }
 }
 
@@ -782,12 +851,19 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 
 __global__ void __launch_bounds__(256) k_grad_reduce_peer(const double* __restrict__ ws, long long ws_stride, const int* __restrict__ goff,
                                                           int kchunk, int d, int Dl, int Dr, int ldA, int ldRpad,
-                                                          const double* __restrict__ tail_local, PeerParams PP,
+                                                          const double* __restrict__ psi_part, int npart, PeerParams PP,
                                                           double* __restrict__ S_out, int* __restrict__ status) {
   const long long nS = (long long)d * Dl * ldA, total = nS + 2;
   const long long per = (total + PEER_CHUNKS - 1) / PEER_CHUNKS;
   const int c = blockIdx.x;
   const long long e0 = (long long)c * per, e1 = e0 + per < total ? e0 + per : total;
+  __shared__ double tail_local[2];
+  if (e1 > nS && e0 < e1) {                                 // block-uniform: this chunk holds the tail
+    __shared__ double sh[9];
+    const double sl = block_total(psi_part, npart, 2, sh), sz = block_total(psi_part + 1, npart, 2, sh);
+    if (threadIdx.x == 0) { tail_local[0] = sl; tail_local[1] = sz; }
+    __syncthreads();
+  }
   constexpr int MAXE = 4;                                   // elements per thread (per <= 1024 for 512 x 512 + 2)
   double mine[MAXE];
   double* my = PP.base[PP.rank] + (long long)PP.slot * PP.slot_elems;
@@ -1059,28 +1135,8 @@ __global__ void __launch_bounds__(256) k_build_perm(const uint8_t* __restrict__ 
 }
 
 // partial sums of squares over the valid region of an engine-layout matrix; part[blockIdx.x]
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  double r = 0.0;
-  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
-  __syncthreads();
-  return r;   // valid in thread 0
-}
-__device__ __forceinline__ double block_max(double v, double* sh) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  double r = -INFINITY;
-  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmax(r, sh[i]);
-  __syncthreads();
-  return r;
-}
-
-constexpr int RED_BLOCKS = 64;
+constexpr int RED_BLOCKS = 148;      // k_sumsq partials
+constexpr int UPD_BLOCKS = 296;      // k_update blocks (4 partials each)
 
 __global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ A, int rows, int ldA, int Dr, int ldRpad,
                                                double* __restrict__ part) {
@@ -1095,18 +1151,22 @@ __global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ A, int
   if (threadIdx.x == 0) part[blockIdx.x] = r;
 }
 
-// A2 = A - lr * (A/Z - S/batch + mom);  partials: [0] max(A2) (signed), [1] sum A2^2, [2] sum dNLL, [3] nonfinite count
+// A2 = A - lr * (A/Z - S/batch + mom);  partials: [0] max(A2) (signed), [1] sum A2^2, [2] sum dNLL, [3] nonfinite count.
+// Z = sum of the nZ partials in partZ.  If tail[1] (number of samples with psi == 0) is positive the descent is skipped
+// (lr = 0) but the tensor is still renormalised and split, as the reference does (TNutils.py:1244-1254).
 __global__ void __launch_bounds__(256) k_update(const double* __restrict__ A, const double* __restrict__ S,
-                                                const double* __restrict__ partZ, int rows, int ldA, int Dr, int ldRpad,
+                                                const double* __restrict__ partZ, int nZ, const double* __restrict__ tail,
+                                                int rows, int ldA, int Dr, int ldRpad,
                                                 double batch, double lr, double mom, double* __restrict__ A2,
                                                 double* __restrict__ part2, double* __restrict__ scal) {
-  __shared__ double sh[8];
-  __shared__ double Zs;
-  if (threadIdx.x == 0) { double z = 0.0; for (int i = 0; i < RED_BLOCKS; ++i) z += partZ[i]; Zs = z; if (blockIdx.x == 0) scal[0] = z; }
-  __syncthreads();
-  const double Z = Zs;
+  __shared__ double sh[9];
+  const double Z = block_total(partZ, nZ, 1, sh);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[0] = Z;
+  if (tail && tail[1] > 0.0) { lr = 0.0; mom = 0.0; }
   const long long total = (long long)rows * ldA;
   double mx = -INFINITY, ss = 0.0, sd = 0.0, nf = 0.0;
+  const double rZ = 1.0 / Z, rB = 1.0 / batch;
+  (void)rZ; (void)rB;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
     int c = (int)(e % ldA) % ldRpad;
     double out = 0.0;
@@ -1130,19 +1190,16 @@ __global__ void __launch_bounds__(256) k_update(const double* __restrict__ A, co
 //   transposed == 0: column-major (rows x ncols): W[cc*rows + r]          (cuSOLVER gesvdj input; Gram on the right side)
 //   transposed == 1: column-major (ncols x rows) = A^T: W[r*ncols + cc]    (Gram on the left side)
 // scal[4]=mean dNLL, [5]=c, [7]=nonfinite
-__global__ void __launch_bounds__(256) k_scale_to_colmajor(const double* __restrict__ A2, const double* __restrict__ part2,
+__global__ void __launch_bounds__(256) k_scale_to_colmajor(const double* __restrict__ A2, const double* __restrict__ part2, int npart,
                                                            int rows, int ldA, int d, int Dr, int ldRpad, int renorm,
                                                            int transposed, double* __restrict__ W, double* __restrict__ scal) {
-  __shared__ double cs;
-  if (threadIdx.x == 0) {
-    double mx = -INFINITY, ss = 0.0, sd = 0.0, nf = 0.0;
-    for (int i = 0; i < RED_BLOCKS; ++i) { mx = fmax(mx, part2[i * 4]); ss += part2[i * 4 + 1]; sd += part2[i * 4 + 2]; nf += part2[i * 4 + 3]; }
-    double c = renorm == 0 ? mx : (renorm == 1 ? sqrt(ss) : 1.0);
-    cs = c;
-    if (blockIdx.x == 0) { scal[4] = sd / ((double)rows * d * Dr); scal[5] = c; scal[7] = nf; }
+  __shared__ double sh[9];
+  const double mx = block_total_max(part2, npart, 4, sh), ss = block_total(part2 + 1, npart, 4, sh);
+  const double c = renorm == 0 ? mx : (renorm == 1 ? sqrt(ss) : 1.0);
+  if (blockIdx.x == 0) {
+    const double sd = block_total(part2 + 2, npart, 4, sh), nf = block_total(part2 + 3, npart, 4, sh);
+    if (threadIdx.x == 0) { scal[4] = sd / ((double)rows * d * Dr); scal[5] = c; scal[7] = nf; }
   }
-  __syncthreads();
-  const double c = cs;
   const int ncols = d * Dr;
   const long long total = (long long)rows * ncols;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {

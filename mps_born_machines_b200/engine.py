@@ -14,7 +14,7 @@ import torch
 
 from . import _capi
 from .parallel import allreduce_sum_
-from ._capi import RENORM, RULE, SVD, ZeroPsiError, check, lib
+from ._capi import RENORM, RULE, SVD, check, lib
 
 SCALAR_NAMES = ('Z', 'sum_logpsi', 'n_zero_psi', 'chi', 'mean_dnll', 'renorm_div', 'trunc_err', 'nonfinite')
 
@@ -191,30 +191,47 @@ class BornEngine:
                                         RENORM[renorm], 1 if going_right else 0,
                                         int(max_bond) if max_bond else 0, float(cutoff), float(mom_bias),
                                         _ptr(scal), _ptr(s) if want_s else None)
+        check(self._ctx, code)
+        return self._step_result(scal, s, want_s)
+
+    @staticmethod
+    def _step_result(scal, s, want_s):
         out = dict(zip(SCALAR_NAMES, scal))
         out['chi'] = int(out['chi'])
         if want_s:
             out['s_all'] = s
             out['s'] = s[:out['chi']]
-        try:
-            check(self._ctx, code)
-        except ZeroPsiError:
-            out['skipped'] = True
-            return out
-        out['skipped'] = False
+        # psi == 0 for some sample: the descent was skipped (lr = 0) but the tensor was renormalised and split,
+        # exactly as the reference does (TNutils.py:1244-1254)
+        out['skipped'] = out['n_zero_psi'] > 0
         return out
 
     def step(self, k, lr, going_right=True, renorm='max', max_bond=None, cutoff=1e-10, mask=None, mom_bias=0.0,
              want_s=False, batch_total=None, advance=True):
-        """One learning_step_cached + write-back + sequential_update (TNutils.py:1603-1620)."""
-        S = self.step_grad(k, mask)
-        if self.world > 1 and not self.peer:
-            allreduce_sum_(S, self.group)   # sum over sample shards (NCCL over NVLink); peer mode: already reduced in-kernel
+        """One learning_step_cached + write-back + sequential_update (TNutils.py:1603-1620).  Single GPU and the
+        fused peer all-reduce run the whole step inside ONE library call (bm_step); the NCCL path needs the collective
+        between the gradient and the update and goes through step_grad / step_update."""
         if batch_total is None:
             batch_total = self.N_total if mask is None else len(mask) * self.world
-        out = self.step_update(k, S, batch_total, lr, going_right, renorm, max_bond, cutoff, mom_bias, want_s)
-        if advance:
-            self.env_advance(k, going_right)
+        if self.world > 1 and not self.peer:
+            S = self.step_grad(k, mask)
+            allreduce_sum_(S, self.group)   # sum over sample shards (NCCL over NVLink)
+            out = self.step_update(k, S, batch_total, lr, going_right, renorm, max_bond, cutoff, mom_bias, want_s)
+            if advance:
+                self.env_advance(k, going_right)
+        else:
+            rows, ld, Dl, Dr, _ = self.grad_dims(k)
+            scal = np.zeros(8)
+            s = np.empty(min(rows, self.d * Dr)) if want_s else None
+            m = None
+            if mask is not None:
+                m = np.ascontiguousarray(np.asarray(mask), dtype=np.int32)
+            code = self._lib.bm_step(self._ctx, k, _ptr(m) if m is not None else None, m.size if m is not None else 0,
+                                     C.c_void_p(self._S.data_ptr()), float(batch_total), float(lr), RENORM[renorm],
+                                     1 if going_right else 0, int(max_bond) if max_bond else 0, float(cutoff),
+                                     float(mom_bias), 1 if advance else 0, _ptr(scal), _ptr(s) if want_s else None)
+            check(self._ctx, code)
+            out = self._step_result(scal, s, want_s)
         out['nll_batch'] = -2.0 * out['sum_logpsi'] / batch_total + math.log(out['Z']) if out['Z'] > 0 else float('nan')
         return out
 
