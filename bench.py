@@ -23,6 +23,13 @@ import tempfile
 import threading
 import time
 
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm (numpy on the host cores) must use
+# all of them, so the BLAS/OpenMP pools are sized BEFORE numpy is imported (the N>1 reference lines ran
+# on one thread).  Our own arm does not compute on the host; its CPU baseline leg (N=1 only) wants the same.
+if '--impl' in sys.argv and 'reference' in sys.argv or os.environ.get('OMP_NUM_THREADS') == '1':
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,7 +44,52 @@ WORKLOADS = {
     'tiny': (512, 64, 32, 24),
 }
 PHYS_DIM = {'c5': 4}
-FP64_PEAK_TFLOPS = 35.7   # measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_probe_fp64_svd.jsonl)
+FP64_PEAK_FALLBACK = 35.7  # cuBLAS DGEMM 8192^3 sustained, measured on this pool in round 1 (profiles/r01_probe_fp64_svd.jsonl);
+                           # only used when the live probe below cannot run
+
+
+def fp64_peak_live(device):
+    """FP64 roofline denominator measured IN THIS RUN: sustained cuBLAS DGEMM (torch.matmul, float64, 8192^3) on the
+    bench GPU, CUDA events, best of 3 after a warm-up.  FP64 is not in the driver-written MEASURED_PEAKS.json and
+    tcgen05 has no FP64 kind, so the library DGEMM is the reference point for DMMA kernels."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randn(n, n, dtype=torch.float64, device=device)
+        b = torch.randn(n, n, dtype=torch.float64, device=device)
+        c = torch.empty(n, n, dtype=torch.float64, device=device)
+        torch.matmul(a, b, out=c)
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        del a, b, c
+        torch.cuda.empty_cache()
+        return best, 'live: cuBLAS DGEMM 8192^3 (torch.matmul float64) timed in this run, best of 3'
+    except Exception as exc:      # e.g. not enough free memory next to the environment stack
+        return FP64_PEAK_FALLBACK, f'fallback 35.7 (round-1 probe; live probe failed: {exc})'
+
+
+def ncu_traffic(kernel, workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    of this round (profiles/r02_ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when no
+    capture exists for this exact kernel/workload/GPU count."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')) as f:
+            tab = json.load(f)
+        ent = tab.get(f'{workload}:{world}', {}).get(kernel)
+        return (ent['dram_bytes'], ent.get('source')) if ent else (None, None)
+    except Exception:
+        return None, None
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(x.get('num_threads', 1)) for x in threadpool_info()] or [1])
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -172,10 +224,12 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'sample_site_updates_per_s_two_site_sweep', 'value': value,
         'unit': 'sample·site updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': workload_config(args.workload, 1),
+        'data': 'synthetic', 'config': workload_config(args.workload, int(os.environ.get('WORLD_SIZE', args.gpus))),
         'cpu_baseline': {'value': value, 'unit': 'sample·site updates/s', 'cores': cores, 'kind': 'port',
+                         'blas_threads': blas_threads(),
                          'sample': f'{args.steps} mid-chain two-site steps (psi+grad+SVD+env advance) at N={N}, D={D}, '
-                                   f'numpy float64 oracle port, BLAS threads = all {cores} host cores'},
+                                   f'numpy float64 oracle port, BLAS pool = {blas_threads()} threads on {cores} host cores '
+                                   f'(OMP_NUM_THREADS reset from the launcher default before numpy was imported)'},
         'e2e': {'value': value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -192,27 +246,25 @@ def workload_config(name, world):
 
 
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args):
+def measure_steps(args, workload, rank, world, local, full=True):
+    """Set up `workload` on this rank's shard and time `args.steps` mid-chain two-site steps (device-resident inputs,
+    CUDA events per step).  full=True adds the e2e loops, the per-kernel roofline pass, the full-chain sweep and the
+    secondary sampler measurement (the headline line); full=False returns the compact record used for the other
+    BASELINE configs."""
     import torch
     import torch.distributed as dist
     from mps_born_machines_b200 import BornEngine
     from mps_born_machines_b200 import mpslib
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
-    N, L, D, k0 = WORKLOADS[args.workload]
-    if args.samples:
+    N, L, D, k0 = WORKLOADS[workload]
+    if args.samples and full:
         N = args.samples
     steps, warm = args.steps, args.warmup
-    assert k0 + warm + 2 * steps + 8 < L - 2, 'not enough sites for the requested number of steps'
+    assert k0 + warm + 3 * steps + 16 < L - 2, 'not enough sites for the requested number of steps'
 
     # ---- set-up (untimed): data shard, MPS with the centre at the first bond, environments
     t_setup = time.time()
-    d = PHYS_DIM.get(args.workload, 2)
+    d = PHYS_DIM.get(workload, 2)
     if d == 2:
         imgs = mpslib.synthetic_images(N, L)
     else:   # 4-level synthetic images: two independent bit planes of the prototype mixture
@@ -242,10 +294,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=f'cuda:{local}')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     kw = dict(renorm='l2', max_bond=D, cutoff=1e-10)
     k = start
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and full:
         clocks.start()                    # live before the warm-up: the timed region is shorter than its start-up
     for _ in range(warm):
         eng.step(k, 1e-3, True, **kw); k += 1
@@ -271,17 +329,47 @@ def run_ours(args):
     wall = time.perf_counter() - wall0
     clocks.mark()
     step_ms = [round(a.elapsed_time(b), 3) for a, b in ev]
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = eng.launch_count() - l0
     eig1 = eng.eig_stats()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=f'cuda:{local}')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    clk = clocks.stop() if rank == 0 else {}
+    dev_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    clk = clocks.stop() if (rank == 0 and full) else {}
     value = N * steps / (dev_ms * 1e-3)
+    rec = {'value': value, 'ms_per_step': dev_ms / steps, 'step_ms': step_ms, 'gram_levels': levels, 'chi': int(chis[-1]),
+           'gpu_launches': int(launches), 'split_eig': {'on_chip': eig1[0] - eig0[0], 'cusolver_fallback': eig1[1] - eig0[1]},
+           'wall_s_timed': wall, 'setup_s': t_setup, 'allreduce': allreduce_mode, 'clocks': clk, 'N': N, 'L': L, 'D': D, 'd': d}
+    if not full:
+        eng.set_timing(True)
+        for _ in range(3):
+            eng.step(k, 1e-3, True, **kw); k += 1
+        tim = eng.get_timing(); eng.set_timing(False)
+        rec['kernel_ms'] = {n: tim[n][0] / tim[n][1] for n in ('grad', 'psi', 'env_advance', 'merge', 'svd') if tim[n][1]}
+        eng.close()
+        return rec
 
-    # ---- e2e: the reference-style call with HOST (pinned) site tensors in and out, every step
+    # ---- e2e (a): the reference's own call sequence through the facade with HOST tensors, every step:
+    #      learning_step_cached -> write the two tensors back into the host MPS -> sequential_update
+    #      (TNutils.py:1603-1620).  Uploads 4 site tensors and downloads 2 per step (pageable numpy memory, as a
+    #      notebook user would hold it).
+    from mps_born_machines_b200 import TNutils as T
+    fmps = T.MPS(eng.get_mps())
+    cache = T.ImgCache(eng, shard)
+    site_bytes = lambda j: int(fmps.tensors[j].data.nbytes)
+    h2d = d2h = 0
+    barrier()
+    e0 = time.perf_counter()
+    for i in range(steps):
+        h2d += 2 * (site_bytes(k) + site_bytes(k + 1))
+        tn = T.learning_step_cached(fmps, k, None, 1e-3, cache, True, **kw)
+        T._write_back(fmps, k, tn)
+        T.sequential_update(fmps, None, cache, k, True)
+        d2h += site_bytes(k) + site_bytes(k + 1) + 64
+        k += 1
+    barrier()
+    e2e_value = N * steps / max_over_ranks(time.perf_counter() - e0)
+    e2e = {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps, 'd2h_bytes_per_step': d2h // steps,
+           'api': 'facade TNutils.learning_step_cached + write-back + sequential_update, host numpy tensors in and out'}
+
+    # ---- e2e (b): the engine-level call with PINNED host site tensors (BornEngine.learning_step_host)
     host = {}
     def pinned(a):
         tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -299,11 +387,10 @@ def run_ours(args):
         host[k + 1] = nb
         k += 1
     barrier()
-    e2e_s = time.perf_counter() - e0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=f'cuda:{local}')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = N * steps / float(t.item())
+    rec['e2e_engine_api'] = {'value': N * steps / max_over_ranks(time.perf_counter() - e0), 'unit': 'sample·site updates/s',
+                             'h2d_bytes_per_step': h2d // steps, 'd2h_bytes_per_step': d2h // steps,
+                             'api': 'BornEngine.learning_step_host, pinned host site tensors'}
+    rec['e2e'] = e2e
 
     # ---- per-kernel pass for the roofline (separate, events around each hot launch)
     eng.set_timing(True)
@@ -323,29 +410,77 @@ def run_ours(args):
             ker[name] = {'ms': ms / cnt}
     dom = max(('grad', 'psi', 'env_advance'), key=lambda n: ker.get(n, {'ms': 0})['ms'])
     peaks, peak_src = load_peaks()
-    # dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/r01_ncu_summary.md);
-    # only valid for the configuration that was captured (c3, one GPU, FP64)
-    traffic = 255.7e6 if (args.workload == 'c3' and world == 1 and not args.samples and dom == 'psi') else None
-    roofline = {'bound': 'tensor', 'kernel': 'k_' + dom, 'achieved': ker[dom]['tflops'], 'peak': FP64_PEAK_TFLOPS,
-                'unit': 'TFLOP/s', 'frac': ker[dom]['tflops'] / FP64_PEAK_TFLOPS, 'traffic': traffic,
-                'peak_source': 'FP64: cuBLAS DGEMM 8192^3 sustained measured by tools/probe on this pool (FP64 is not in '
-                               'MEASURED_PEAKS.json; tcgen05 has no FP64 kind, DMMA.8x8x4 issue peak measured 37.1); '
-                               f'MEASURED_PEAKS.json {peak_src}',
-                'algorithmic_flops_per_launch': 2.0 * D * D * n_loc, 'kernels': ker}
+    fp64_peak, fp64_src = fp64_peak_live(f'cuda:{local}')
+    traffic, traffic_src = ncu_traffic('k_' + dom, workload if not args.samples else 'custom', world)
+    rec['roofline'] = {'bound': 'tensor', 'kernel': 'k_' + dom, 'achieved': ker[dom]['tflops'], 'peak': fp64_peak,
+                       'unit': 'TFLOP/s', 'frac': ker[dom]['tflops'] / fp64_peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                       'peak_source': f'FP64 {fp64_src} (FP64 is not in MEASURED_PEAKS.json [{peak_src}]; tcgen05 has no FP64 kind: DMMA.8x8x4)',
+                       'algorithmic_flops_per_launch': 2.0 * D * D * n_loc,
+                       'algorithmic_bytes_per_launch': 2.0 * D * 8 * n_loc, 'kernels': ker,
+                       'whole_step_tflops': 6.0 * D * D * n_loc / (dev_ms / steps * 1e-3) / 1e12,
+                       'whole_step_frac': 6.0 * D * D * n_loc / (dev_ms / steps * 1e-3) / 1e12 / fp64_peak}
+
+    # ---- a FULL two-site sweep (there and back, 2(L-1) steps over the whole chain incl. the narrow bonds at the ends),
+    #      timed on the device as one region: the north star's sweeps/s, measured instead of extrapolated
+    if not args.no_sweep:
+        mps0 = mpslib.random_mps(L, D, d=d, rng=np.random.default_rng(12), centre=0)
+        eng.set_mps(mps0)
+        eng.env_build(0)
+        e0s, e1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0s.record()
+        outs = eng.epoch(1e-3, **kw)
+        e1s.record()
+        barrier()
+        sw_ms = max_over_ranks(e0s.elapsed_time(e1s))
+        rec['full_sweep'] = {'seconds': sw_ms * 1e-3, 'steps': len(outs), 'sweeps_per_s': 1e3 / sw_ms,
+                             'value': N * len(outs) / (sw_ms * 1e-3), 'unit': 'sample·site updates/s',
+                             'skipped_steps': int(sum(1 for o_ in outs if o_['skipped'])),
+                             'max_chi': int(max(o_['chi'] for o_ in outs))}
 
     # ---- secondary metric of BASELINE.json: samples generated / s (batched ancestral sampler, device-resident).
-    #      Reuses this engine: the chain right of the current centre is right-canonical, and the sampler's arithmetic
-    #      and cost do not depend on the gauge of the left part (the full config-4 run is `--workload c4`).
-    sampler = None
+    #      Reuses this engine: the sampler's arithmetic and cost do not depend on the gauge (config 4 itself is below).
     if world == 1 and not args.no_sampler:
         ns = 20000
         eng.sample_device_ms(2048, seed=3)
         ms_s = [eng.sample_device_ms(ns, seed=7 + i) for i in range(2)]
-        sampler = {'metric': 'samples_generated_per_s', 'value': ns / (min(ms_s) * 1e-3), 'unit': 'samples/s',
-                   'n_samples': ns, 'sites': L, 'Dmax': D, 'ms': min(ms_s),
-                   'tflops_executed': 2.0 * D * D * 2.0 * L * ns / (min(ms_s) * 1e-3) / 1e12,
-                   'note': 'generate_samples (TNutils.py:1829) on the bench MPS, uniforms generated on device; config 4 '
-                           '(D=500, N=100k): python bench.py --workload c4 -> 34.5k samples/s (profiles/r01_bench_c4_sampler.json)'}
+        rec['sampler'] = {'metric': 'samples_generated_per_s', 'value': ns / (min(ms_s) * 1e-3), 'unit': 'samples/s',
+                          'n_samples': ns, 'sites': L, 'Dmax': D, 'ms': min(ms_s),
+                          'tflops_executed': 2.0 * D * D * 2.0 * L * ns / (min(ms_s) * 1e-3) / 1e12,
+                          'note': 'generate_samples (TNutils.py:1829) on the bench MPS, uniforms generated on device'}
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+    rec = measure_steps(args, args.workload, rank, world, local, full=True)
+    N, D, d, L = rec['N'], rec['D'], rec['d'], rec['L']
+
+    # ---- the other BASELINE configs that fit one GPU, each as a short run of the same measurement (N=1 only)
+    others = {}
+    if world == 1 and args.workload == 'c3' and not args.samples and not args.no_others:
+        for w in ('c2', 'c5', 'c5b'):
+            try:
+                r = measure_steps(args, w, rank, world, local, full=False)
+                others[w] = {'workload': workload_config(w, 1)['workload'], 'ms_per_step': r['ms_per_step'], 'value': r['value'],
+                             'unit': 'sample·site updates/s', 'chi': r['chi'], 'split_eig': r['split_eig'], 'kernel_ms': r['kernel_ms'],
+                             'gram_levels': r['gram_levels']}
+            except Exception as exc:
+                others[w] = {'error': str(exc)}
+        try:
+            others['c4'] = sampler_record(args, rank, world, local, n_samples=100000, steps=1)
+        except Exception as exc:
+            others['c4'] = {'error': str(exc)}
 
     if rank == 0:
         cpu = None
@@ -353,40 +488,38 @@ def run_ours(args):
             cs = max(2, min(8, int(20.0 / max(0.05, 1.5e-5 * N * D / 256))))
             tcpu = cpu_reference_steps(N, D, cs, d=d)
             cpu = {'value': N / float(np.mean(tcpu)), 'unit': 'sample·site updates/s', 'cores': os.cpu_count(), 'kind': 'port',
-                   'sample': f'{cs} mid-chain two-site steps at N={N}, D={D} (numpy float64 oracle port, all host cores)'}
+                   'blas_threads': blas_threads(),
+                   'sample': f'{cs} mid-chain two-site steps at N={N}, D={D} (numpy float64 oracle port, BLAS pool sized to all host cores)'}
         line = {
-            'metric': 'sample_site_updates_per_s_two_site_sweep', 'value': value, 'unit': 'sample·site updates/s',
-            'n_gpus': world, 'steps': steps, 'warmup': warm, 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
+            'metric': 'sample_site_updates_per_s_two_site_sweep', 'value': rec['value'], 'unit': 'sample·site updates/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': rec['ms_per_step'], 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64' if args.precision == 'fp64' else 'f64 (gradient accumulation: tf32 operands, f32 TMEM accumulators)', 'data': 'synthetic',
             'config': workload_config(args.workload, world),
-            'e2e': {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps,
-                    'd2h_bytes_per_step': d2h // steps},
-            'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clk,
-            'svd': args.svd, 'split_eig': {'on_chip': eig1[0] - eig0[0], 'cusolver_fallback': eig1[1] - eig0[1]}, 'allreduce': allreduce_mode, 'chi': int(chis[-1]), 'step_ms': step_ms, 'gram_levels': levels, 'wall_s_timed': wall, 'setup_s': t_setup,
-            'sweep_s_extrapolated': dev_ms / steps * 1e-3 * 2 * (L - 1),
+            'e2e': rec['e2e'], 'e2e_engine_api': rec['e2e_engine_api'],
+            'gpu_launches': rec['gpu_launches'], 'roofline': rec['roofline'], 'clocks': rec['clocks'],
+            'svd': args.svd, 'split_eig': rec['split_eig'], 'allreduce': rec['allreduce'], 'chi': rec['chi'], 'step_ms': rec['step_ms'],
+            'gram_levels': rec['gram_levels'], 'wall_s_timed': rec['wall_s_timed'], 'setup_s': rec['setup_s'],
+            'sweep_s_extrapolated': rec['ms_per_step'] * 1e-3 * 2 * (L - 1),
         }
+        for key in ('full_sweep', 'sampler'):
+            if key in rec:
+                line[key] = rec[key]
         if cpu:
             line['cpu_baseline'] = cpu
-        if sampler:
-            line['sampler'] = sampler
+        if others:
+            line['other_configs'] = others
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_sampler(args):
+def sampler_record(args, rank, world, local, n_samples, steps):
     """Workload c4: batched ancestral sampling (generate_samples, TNutils.py:1829-1872) of N images from a
     right-canonical random MPS with D=500 (no trained D=500 model ships with the reference).  Metric: samples/s.
     One step = one full pass over the 784 sites for all N samples."""
     import torch
     from mps_born_machines_b200 import BornEngine, mpslib
-    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
-    N, L, D = (args.samples or 100000), 784, args.sampler_bond
+    N, L, D = n_samples, 784, args.sampler_bond
     n_loc = (N + world - 1) // world                      # replicas only: every rank samples its share, no collective
     mps = mpslib.random_mps(L, D, rng=np.random.default_rng(13), centre=0)
     eng = BornEngine(L, D, device=local)
@@ -398,52 +531,69 @@ def run_sampler(args):
         clocks.start()
     l0 = eng.launch_count()
     clocks.mark()
-    ms = [eng.sample_device_ms(n_loc, seed=100 + i) for i in range(args.steps)]
+    ms = [eng.sample_device_ms(n_loc, seed=100 + i) for i in range(steps)]
     clocks.mark()
     launches = eng.launch_count() - l0
     clk = clocks.stop() if rank == 0 else {}
     t = torch.tensor([sum(ms)], dtype=torch.float64, device=f'cuda:{local}')
     if world > 1:
+        import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
-    value = N * args.steps / (dev_ms * 1e-3)
+    value = N * steps / (dev_ms * 1e-3)
     # e2e: host uniforms in (pinned), host samples out, through the public call
     ne = min(n_loc, 16384)
     U = torch.from_numpy(np.random.default_rng(17).random((L, ne))).pin_memory().numpy()
     t0 = time.perf_counter(); out = eng.sample(ne, U=U); e2e_s = time.perf_counter() - t0
     f0 = 1.0 - float(out.mean())
-    flops = 2.0 * D * D * 2.0 * L * N * args.steps            # both branches are evaluated for rejected rows
+    executed = 2.0 * D * D * 2.0 * L * N * steps / (dev_ms * 1e-3) / 1e12     # both branches are evaluated for rejected rows
+    algorithmic = executed * (1.0 + f0) / 2.0    # the reference evaluates branch 1 only for the rows that reject pixel 0
+    peak, peak_src = fp64_peak_live(f'cuda:{local}')
+    eng.close()
+    line = None
     if rank == 0:
         from oracle import born_oracle as o
         nc = 2000
         Uc = np.random.default_rng(17).random((8, nc))
-        mps8 = [m for m in mps[:8]]
         # CPU port of the same per-site work: 8 mid-chain sites at bond D on nc samples, extrapolated to 784 sites
         half = np.random.default_rng(3).standard_normal((nc, D)); m3 = o.site3(mps, 400)
         tc = time.perf_counter()
-        for s in range(8):
+        for s_ in range(8):
             ampl = half @ m3[:, :, 0]
             cond = np.einsum('nb,nb->n', ampl, ampl) / np.einsum('nb,nb->n', half, half)
-            acc = Uc[s] <= cond
+            acc = Uc[s_] <= cond
             new = np.where(acc[:, None], ampl, half @ m3[:, :, 1])
             half = new / np.abs(new).max(axis=1, keepdims=True)
         tc = (time.perf_counter() - tc) / 8 * L
-        line = {'metric': 'samples_generated_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak' if False else 'strong',
+        line = {'metric': 'samples_generated_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': steps,
+                'warmup': args.warmup, 'ms_per_step': dev_ms / steps, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': f'c4: batched ancestral sampling of {N} images, L={L}, right-canonical random MPS D={D}, '
                                        'device-generated uniforms (counter-based), both branches per site', 'n_samples': N, 'Dmax': D,
                            'parallelism': 'replicas only (no collective)', 'l2': f'state 2x{n_loc}x{D}x8 B ping-pong > L2'},
                 'e2e': {'value': ne / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(U.nbytes), 'd2h_bytes_per_step': int(out.nbytes)},
                 'gpu_launches': int(launches),
-                'roofline': {'bound': 'tensor', 'kernel': 'k_sample_step', 'achieved': flops / (dev_ms * 1e-3) / 1e12, 'peak': FP64_PEAK_TFLOPS,
-                             'unit': 'TFLOP/s', 'frac': flops / (dev_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, 'traffic': None,
-                             'note': 'executed flops (both branches); algorithmic credit is 2*D^2*(1+f0) with f0 = %.3f' % f0},
+                'roofline': {'bound': 'tensor', 'kernel': 'k_sample_step', 'achieved': algorithmic, 'executed': executed, 'peak': peak,
+                             'unit': 'TFLOP/s', 'frac': algorithmic / peak, 'frac_executed': executed / peak, 'traffic': None,
+                             'peak_source': peak_src,
+                             'note': 'achieved = ALGORITHMIC flops 2*D^2*(1+f0) per sample and site (f0 = %.3f: share of accepted '
+                                     'pixel-0 draws); the kernel evaluates both branches for every 64-row tile with a rejection' % f0},
                 'clocks': clk,
-                'cpu_baseline': {'value': nc / tc, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                'cpu_baseline': {'value': nc / tc, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port', 'blas_threads': blas_threads(),
                                  'sample': f'8 mid-chain sites at D={D} on {nc} samples (numpy float64 port of generate_samples), x{L}/8'}}
+    return line
+
+
+def run_sampler(args):
+    import torch
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+    line = sampler_record(args, rank, world, local, args.samples or 100000, args.steps)
+    if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
 
 
 def main():
@@ -457,6 +607,8 @@ def main():
     ap.add_argument('--svd', default='gram', choices=['gram', 'gram_syevd', 'gesvdj'])
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-sampler', action='store_true', help='skip the secondary samples/s measurement')
+    ap.add_argument('--no-sweep', action='store_true', help='skip the full 2(L-1)-step sweep measurement')
+    ap.add_argument('--no-others', action='store_true', help='skip the short runs of BASELINE configs 2, 4, 5')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
                     help='multi-GPU gradient exchange: fused reduce + peer-memory all-reduce kernel, or NCCL')
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32'],

@@ -149,7 +149,9 @@ class MPS:
         return self.copy()
 
     def bond_sizes(self):
-        return [mpslib.site3(self.arrays(), k).shape[1] for k in range(self.L - 1)]
+        # right bond of site k straight from the stored shapes: (Dr, d) at site 0, (Dl, Dr, d) elsewhere
+        return [t.data.shape[0] if (k == 0 and t.data.ndim == 2) else t.data.shape[1]
+                for k, t in enumerate(self.tensors[:-1])]
 
     def max_bond(self):
         return max(self.bond_sizes())
@@ -370,19 +372,37 @@ def _engine_for(mps, pixels, max_bond=None):
 
 def left_right_cache(mps, _imgs, max_bond=None):
     """TNutils.py:457-481.  `max_bond` (extension) sizes the device buffers for later bond growth; the cache is
-    re-created transparently by learning_epoch_cached when `max_bond=` exceeds it."""
+    re-created transparently by the learning functions when a step needs more room (an explicit `max_bond=` above the
+    capacity, or NO `max_bond`: the reference then lets the bond grow to d*min(Dl, Dr), limited only by `cutoff`)."""
     pixels = _to_pixels(_imgs)
     eng = _engine_for(mps, pixels, max_bond)
     eng.env_build(0)
     return ImgCache(eng, pixels)
 
 
-def _ensure_capacity(mps, img_cache, max_bond):
-    need = max(int(max_bond or 0), mps.max_bond())
-    if need > img_cache.engine.Dcap:
-        img_cache.engine.close()
-        img_cache.engine = _engine_for(mps, img_cache.pixels, need)
-    return img_cache.engine
+def _ensure_capacity(mps, img_cache, max_bond, index=None, dims=None):
+    """Make sure the device buffers can hold the bond this step may produce.  With `max_bond=None` the reference's
+    `A.split(cutoff=1e-10)` (TNutils.py:1552-1564) keeps up to min(d*Dl, d*Dr) values, so the engine must not clamp
+    at its initial capacity: it is re-created with (at least) twice the capacity whenever bond `index` could outgrow
+    it.  `dims` = (Dl of site index, Dr of site index+1) when the caller knows them (the sites may live on the
+    device only); returns (engine, recreated)."""
+    eng = img_cache.engine
+    need = max(int(max_bond or 0), 2)
+    if not max_bond and index is not None:
+        if dims is None:
+            a, b = mps.tensors[index].data, mps.tensors[index + 1].data
+            dims = (1 if index == 0 else a.shape[0], 1 if index + 1 == len(mps.tensors) - 1 else b.shape[1])
+        need = eng.d * min(dims)
+    if need <= eng.Dcap:
+        return eng, False
+    arrays = [t.data for t in mps.tensors]
+    need = max(need, max(MPS(arrays).bond_sizes())) if max_bond else max(need, 2 * eng.Dcap)
+    eng.close()
+    new = BornEngine(len(mps.tensors), need, phys_dim=eng.d)
+    new.set_mps(arrays)
+    new.set_data(img_cache.pixels)
+    img_cache.engine = new
+    return new, True
 
 
 def sequential_update(mps, _imgs, img_cache, site, going_right):
@@ -440,7 +460,9 @@ def learning_step_cached(mps, index, _imgs, lr, img_cache, going_right=True,
     identity run on the host (download dNLL, call, upload) — the reference's momentum (`mps_lr.J`) is recognised
     and evaluated on the device instead."""
     max_bond, cutoff = kwargs.get('max_bond'), kwargs.get('cutoff', 1e-10)
-    eng = _ensure_capacity(mps, img_cache, max_bond)
+    eng, recreated = _ensure_capacity(mps, img_cache, max_bond, index)
+    if recreated:
+        eng.env_build(index)
     eng.set_site(index, mps.tensors[index].data)
     eng.set_site(index + 1, mps.tensors[index + 1].data)
     mask = img_cache.mask
@@ -535,8 +557,9 @@ def learning_epoch_cached(mps, *args, batch_size=25, update_wrap=None, lr_update
     batch_size = min(n, batch_size)
     guide = np.arange(n)
     max_bond, cutoff = kwargs.get('max_bond'), kwargs.get('cutoff', 1e-10)
-    eng = _ensure_capacity(mps, img_cache, max_bond)
+    eng, _ = _ensure_capacity(mps, img_cache, max_bond)
     eng.set_mps(mps.arrays())
+    eng.env_build(0)
     owner = None
     generic = False
     if update_wrap is not None and not _is_identity(update_wrap):
@@ -556,6 +579,11 @@ def learning_epoch_cached(mps, *args, batch_size=25, update_wrap=None, lr_update
                 np.random.shuffle(guide)
                 mask = guide[:batch_size].copy()
             mom = owner.momentum * owner.past_grad[index] if (owner is not None and owner.t > 0) else 0.0
+            if not max_bond:             # unbounded growth (cutoff only): make room before the bond can outgrow the buffers
+                dims = (eng.site_dims(index)[0], eng.site_dims(index + 1)[1])
+                if eng.d * min(dims) > eng.Dcap:
+                    mps._set(eng.get_mps())
+                    eng, _ = _ensure_capacity(mps, img_cache, None, index, dims)   # environments are rebuilt by the step
             if generic:
                 out = eng.step_with_update_fn(index, _lr_value(lr), lambda site, dn: _as_array(update_wrap(site, _dnll_tensor(site, dn, L))).reshape(dn.shape),
                                               going_right, renorm, max_bond, cutoff, mask)

@@ -29,7 +29,8 @@ def sweep_schedule(L):
 
 
 class BornEngine:
-    def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gram', dist_group=None, precision='fp64'):
+    def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gram', dist_group=None, precision='fp64',
+                 standalone=False):
         if not torch.cuda.is_available():
             raise RuntimeError('BornEngine needs a CUDA device (sm_100a); there is no CPU fallback')
         self.L, self.d, self.Dcap = int(n_sites), int(phys_dim), int(max_bond)
@@ -52,7 +53,9 @@ class BornEngine:
         self.peer = False
         self.group = dist_group
         self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        # standalone=True: an engine that holds ALL its data and never takes part in a collective, even inside a
+        # multi-rank job (the single-GPU reference of the multi-GPU parity checks)
+        if not standalone and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(dist_group)
 
     def enable_peer_allreduce(self):
@@ -109,9 +112,21 @@ class BornEngine:
         if a.min() < 0 or a.max() >= self.d:
             raise ValueError('training images must hold levels 0..d-1 (no unknown pixels)')
         px = np.ascontiguousarray(a.astype(np.uint8))
+        # every rank learns every shard size: the global batch size of a step must be the same number on all ranks
+        # (shards may be uneven), otherwise the replicated update diverges silently
+        self.shard_sizes = [px.shape[0]]
+        if self.world > 1:
+            sizes = [None] * self.world
+            torch.distributed.all_gather_object(sizes, int(px.shape[0]), group=self.group)
+            self.shard_sizes = [int(x) for x in sizes]
+        if min(self.shard_sizes) < 1:
+            raise ValueError(f'every rank needs at least one training sample (shard sizes {self.shard_sizes}); '
+                             'use fewer ranks or parallel.shard_bounds on a larger data set')
         check(self._ctx, self._lib.bm_set_data(self._ctx, _ptr(px), px.shape[0]))
         self.N = px.shape[0]
-        self.N_total = int(n_total) if n_total is not None else self.N * self.world
+        self.N_total = sum(self.shard_sizes)
+        if n_total is not None and int(n_total) != self.N_total:
+            raise ValueError(f'n_total={n_total} does not match the sum of the shard sizes {self.shard_sizes}')
 
     def set_site(self, k, t):
         t = np.asarray(t, dtype=np.float64)
@@ -212,7 +227,10 @@ class BornEngine:
         fused peer all-reduce run the whole step inside ONE library call (bm_step); the NCCL path needs the collective
         between the gradient and the update and goes through step_grad / step_update."""
         if batch_total is None:
-            batch_total = self.N_total if mask is None else len(mask) * self.world
+            if mask is not None and self.world > 1:
+                raise ValueError('multi-rank minibatch steps need batch_total (the global number of samples used by '
+                                 'this step, identical on every rank): see BornEngine.epoch')
+            batch_total = self.N_total if mask is None else len(mask)
         if self.world > 1 and not self.peer:
             S = self.step_grad(k, mask)
             allreduce_sum_(S, self.group)   # sum over sample shards (NCCL over NVLink)
@@ -273,7 +291,9 @@ class BornEngine:
         S = self.step_grad(k, mask)
         if self.world > 1 and not self.peer:
             allreduce_sum_(S, self.group)
-        B = self.N_total if mask is None else len(mask) * self.world
+        if mask is not None and self.world > 1:
+            raise ValueError('step_with_update_fn: multi-rank minibatches are not supported (use BornEngine.epoch)')
+        B = self.N_total if mask is None else len(mask)
         A = self.get_merged_at(k)
         Sref = self.grad_to_ref(k, S)
         Z = float(np.sum(A * A))
@@ -307,12 +327,16 @@ class BornEngine:
         L = self.L
         going_right = True
         outs = []
+        # minibatches: `batch_size` samples PER RANK (all of a shard that is smaller).  Whether masks are used and the
+        # global batch size are derived from ALL shard sizes, so every rank applies the same 1/B to the summed gradient.
+        use_mask = batch_size is not None and any(batch_size < n for n in self.shard_sizes)
+        batch_total = sum(min(batch_size, n) for n in self.shard_sizes) if use_mask else None
         for k in sweep_schedule(L):
             mask = None
-            if batch_size is not None and batch_size < self.N:
+            if use_mask and batch_size < self.N:
                 guide = (rng if rng is not None else np.random).permutation(self.N)
                 mask = guide[:batch_size]
-            o = self.step(k, lr, going_right, renorm, max_bond, cutoff, mask)
+            o = self.step(k, lr, going_right, renorm, max_bond, cutoff, mask, batch_total=batch_total)
             if callback is not None:
                 callback(k, going_right, o)
             outs.append(o)

@@ -203,3 +203,25 @@ def test_arbitrary_update_wrap_callback(T):
     cost_o, _ = o.learning_epoch_cached(start, imgs, 2, 0.1, renorm='l2', max_bond=6, update_wrap=lambda k, dn: 0.5 * dn)
     np.testing.assert_allclose(cost, cost_o, rtol=1e-6)
     assert seen[0] == (0, ('v0', 'i1', 'v1')) and seen[1][1] == ('i0', 'v1', 'i2', 'v2') and len(seen) == 2 * 2 * (L - 1)
+
+
+def test_no_max_bond_lets_the_bond_grow(T):
+    """`learning_epoch_cached(...)` / `learning_step_cached(...)` WITHOUT max_bond: the reference's split is limited by
+    cutoff=1e-10 only (TNutils.py:1552-1564), so bonds grow past the initial maximum (the engine must not
+    clamp at its initial capacity).  Same trajectory and bond profile as the oracle."""
+    np.random.seed(9)
+    mps = T.initialize_mps(12, 2)
+    start = [t.copy() for t in mps.arrays()]
+    imgs = (np.random.default_rng(5).random((40, 12)) < 0.4).astype(np.int64)
+    data = np.array([T.tens_picture(img) for img in imgs])
+    cache = T.left_right_cache(mps, data)
+    assert cache.engine.Dcap == 2
+    nlls, _ = T.learning_epoch_cached(mps, data, 2, 0.05, cache, batch_size=40)
+    cost_o, _ = o.learning_epoch_cached(start, imgs, 2, 0.05, batch_size=40, max_bond=None, gauge='fixed')
+    assert max(mps.bond_sizes()) > 2 and cache.engine.Dcap >= max(mps.bond_sizes())
+    np.testing.assert_allclose(nlls, cost_o, rtol=1e-6)
+    # step-level call without max_bond on a fresh model: chi = number of singular values above the cutoff
+    mps2 = T.MPS(start)
+    cache2 = T.left_right_cache(mps2, data)
+    tn = T.learning_step_cached(mps2, 5, data, 0.05, cache2, True)
+    assert tn.tensors[0].data.shape[-1] == tn.info['chi'] > 2

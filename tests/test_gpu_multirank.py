@@ -1,0 +1,67 @@
+"""Multi-rank parity THROUGH libbm.so (the only multi-rank test all-reduced oracle arrays).
+Two processes, each with its own BornEngine on half of the samples; the gradient is summed either by the fused
+peer-memory kernel k_grad_reduce_peer (CUDA IPC) or by torch.distributed.  On a box with one GPU both ranks share
+cuda:0 and the control plane is gloo; with >= 2 GPUs each rank has its own GPU and NCCL is used.
+Reference semantics: the sum over samples of TNutils.py:1526-1541 is split over ranks, nothing else changes."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _run(mode, allreduce, world=2, timeout=600):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'multirank_worker.py'), mode, allreduce],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=timeout))
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            pytest.fail('multi-rank worker timed out')
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-3000:]
+    line = [l for l in outs[0][0].splitlines() if l.startswith('RESULT ')][-1]
+    res = json.loads(line[len('RESULT '):])
+    log = os.path.join(ROOT, 'gpurun_out')
+    if os.path.isdir(log):                      # keep the evidence of the run next to the other GPU artefacts
+        with open(os.path.join(log, 'multirank_parity.jsonl'), 'a') as f:
+            f.write(json.dumps(res) + '\n')
+    return res
+
+
+@pytest.mark.parametrize('allreduce', ['peer', 'dist'])
+def test_two_rank_teacher_forced_steps_match_single_gpu(allreduce):
+    res = _run('teacher', allreduce)
+    assert res['chi_equal']
+    assert res['max_rel_s'] < 1e-6 and res['max_rel_sumlog'] < 1e-9 and res['max_rel_Z'] < 1e-9, res
+    assert res['replica_drift'] == 0.0, res                     # replicas bitwise identical
+
+
+def test_two_rank_free_running_bars_and_stripes_matches_single_gpu():
+    """a well-conditioned problem (no near-zero psi): the free-running 16-epoch NLL curve of the sharded run equals the
+    single-GPU curve to 1e-6."""
+    res = _run('bas', 'peer')
+    np.testing.assert_allclose(res['nll_sharded'], res['nll_single'], rtol=1e-6)
+    assert res['bonds'] == res['bonds_single'] and res['replica_drift'] == 0.0
+    assert np.log(30) < res['nll_sharded'][-1] < np.log(30) + 0.1

@@ -33,8 +33,7 @@ if PEER:
     assert eng.enable_peer_allreduce()
 single = None
 if rank == 0:
-    single = BornEngine(L, D, device=local)
-    single.world = 1                      # full data on one GPU, no collective
+    single = BornEngine(L, D, device=local, standalone=True)   # full data on one GPU, no collective
     single.set_data(imgs, n_total=N)
 worst_s = worst_ln = worst_z = 0.0
 going_right = True
