@@ -152,6 +152,14 @@ int bm_sample(bm_ctx* ctx, int n, int rule, int start_site, const double* U_host
  * u_host: one uniform per unknown pixel, in site order. */
 int bm_reconstruct_one(bm_ctx* ctx, const uint8_t* pixels_host, const double* u_host, int n_unknown, uint8_t* out_host);
 
+/* f3: the same for n_images images that share ONE mask (e.g. partial_removal_img(img, shape, fraction, axis, half) applied
+ * to a whole test set, TNutils.py:211-254 + :2053-2116).  pixels_host [n_images][n_sites] (255 = unknown),
+ * u_host [n_images][n_unknown] (image b's uniforms in site order), out_host [n_images][n_sites].  The right-environment
+ * matrices of all unknown sites stay on the device: n_images * n_unknown * Dcap^2 * 8 bytes; BM_ENOMEM (with the largest
+ * batch that fits in the error text) when that does not fit -- the caller then splits the batch. */
+int bm_reconstruct_batch(bm_ctx* ctx, const uint8_t* pixels_host, int n_images, const double* u_host, int n_unknown,
+                         uint8_t* out_host);
+
 /* Device-resident variants for benchmarking (no host traffic): uniforms generated on device, output
  * left on device.  Returns elapsed device milliseconds of the sampling loop in *ms. */
 int bm_sample_device(bm_ctx* ctx, int n, int rule, uint64_t seed, float* ms);

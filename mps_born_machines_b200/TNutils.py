@@ -660,32 +660,54 @@ def generate_sample(mps):
 def reconstruct(mps, corr_img):
     """TNutils.py:2053-2116.  Known-prefix masks (partial_removal_img axis=0, half=0) take the batched sampler path
     (prefix contracted on the device, remaining sites sampled from the right-canonical tail); any other mask takes
-    the general path (right-environment matrices, bm_reconstruct_one)."""
-    corr_img = np.asarray(corr_img)
-    unknown = np.nonzero(corr_img == -1)[0]
-    if unknown.size == 0:
-        return corr_img.copy()
-    start = int(unknown[0])
-    if not np.all(corr_img[start:] == -1):
-        # general mask: exact conditionals from right-environment matrices on the device (one image at a time, like
-        # the reference); one np.random.rand() per unknown pixel in site order, as generate_sample draws them
-        rec = mps.copy().normalize()
-        u = np.array([np.random.rand() for _ in range(unknown.size)])
-        eng = BornEngine(len(rec.tensors), max(rec.max_bond(), 2))
-        eng.set_mps(rec.arrays())
-        out = eng.reconstruct_one(corr_img, u)
-        eng.close()
-        return out.astype(corr_img.dtype)
-    rec = mps.copy().normalize().right_canonize()
-    L = len(rec.tensors)
-    U = np.array([[np.random.rand()] for _ in range(L - start)])
-    eng = BornEngine(L, max(rec.max_bond(), 2))
-    eng.set_mps(rec.arrays())
-    out = eng.sample(1, U=U, rule='single', prefix=corr_img[None, :] if start > 0 else None, start_site=start)
-    eng.close()
-    res = corr_img.copy()
-    res[start:] = out[0, start:]
-    return res
+    the general path (right-environment matrices, bm_reconstruct_batch with one image)."""
+    return reconstruct_batch(mps, np.asarray(corr_img)[None, :])[0]
+
+
+def reconstruct_batch(mps, corr_imgs):
+    """`[reconstruct(mps, img) for img in corr_imgs]` in one go (extension; the reference reconstructs one image per
+    call, e.g. notebooks/mnist.ipynb loops over the test set).  Draws np.random.rand() exactly as that loop would --
+    image by image, one number per unknown pixel in site order -- so a seeded run returns the same pictures.
+    Images are grouped by mask; each group runs as one batch on the device (known-prefix masks through the batched
+    sampler, any other mask through bm_reconstruct_batch)."""
+    corr = np.asarray(corr_imgs)
+    if corr.ndim != 2 or corr.shape[1] != len(mps.tensors):
+        raise ValueError(f'expected (B,{len(mps.tensors)}) images with -1 for the unknown pixels')
+    out = corr.copy()
+    L = corr.shape[1]
+    masks = corr == -1
+    draws = [np.array([np.random.rand() for _ in range(int(m.sum()))]) for m in masks]    # the reference's draw order
+    groups = {}
+    for b, m in enumerate(masks):
+        if m.any():
+            groups.setdefault(m.tobytes(), []).append(b)
+    if not groups:
+        return out
+    rec = mps.copy().normalize()
+    canon = None
+    for key, ids in groups.items():
+        m = masks[ids[0]]
+        start = int(np.nonzero(m)[0][0])
+        U = np.stack([draws[b] for b in ids])                 # (B, n_unknown)
+        if m[start:].all():                                   # known prefix: batched ancestral sampling of the tail
+            if canon is None:
+                canon = rec.copy().right_canonize()
+                eng_c = BornEngine(L, max(canon.max_bond(), 2))
+                eng_c.set_mps(canon.arrays())
+            got = eng_c.sample(len(ids), U=np.ascontiguousarray(U.T), rule='single',
+                               prefix=corr[ids] if start > 0 else None, start_site=start)
+            for i, b in enumerate(ids):
+                out[b, start:] = got[i, start:]
+        else:
+            eng = BornEngine(L, max(rec.max_bond(), 2))
+            eng.set_mps(rec.arrays())
+            got = eng.reconstruct_batch(corr[ids], U)
+            eng.close()
+            for i, b in enumerate(ids):
+                out[b] = got[i]
+    if canon is not None:
+        eng_c.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------

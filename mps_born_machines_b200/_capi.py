@@ -43,6 +43,7 @@ _SIGS = [
     ('bm_last_logpsi', C.c_int, [_P, _P]),
     ('bm_sample', C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_uint64, _P, _P]),
     ('bm_reconstruct_one', C.c_int, [_P, _P, _P, C.c_int, _P]),
+    ('bm_reconstruct_batch', C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     ('bm_sample_device', C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_float)]),
     ('bm_peer_export', C.c_int, [_P, _P]),
     ('bm_peer_import', C.c_int, [_P, _P, C.c_int, C.c_int]),

@@ -112,9 +112,11 @@ struct bm_ctx {
   double* peer_buf = nullptr; size_t peer_slot_elems = 0; int peer_world = 0, peer_rank = 0;
   double* peer_base[PEER_MAX] = {nullptr}; void* peer_opened[PEER_MAX] = {nullptr};
   unsigned long long peer_step = 0; double* tail_local = nullptr;
-  // general-mask reconstruction: right-environment matrices E_j (row-major Dcap x Dcap each), vectors, counters
-  double* recE = nullptr; double* recT = nullptr; double* recV[2] = {nullptr, nullptr}; double* recU = nullptr;
-  uint8_t* recPix = nullptr; int* recCount = nullptr;
+  // general-mask reconstruction (bm_reconstruct_batch): right-environment matrices E_j (row-major Dcap x ldcap each)
+  // batched version: E slots of the unknown sites, ping-pong current E, T, vectors, selectors (grow-only)
+  double* rbEst = nullptr; size_t rbEst_cap = 0; double* rbEc[2] = {nullptr, nullptr}; double* rbT = nullptr; size_t rbE_cap = 0;
+  double* rbV[2] = {nullptr, nullptr}; size_t rbV_cap = 0; double* rbU = nullptr; size_t rbU_cap = 0;
+  uint8_t* rbPix = nullptr; int* rbSel = nullptr; size_t rbPix_cap = 0;
 
   // optional per-kernel timing (bm_set_timing): CUDA events on the launch stream around each hot kernel
   int timing = 0;
@@ -209,7 +211,8 @@ int set_func_attrs(bm_ctx* c) {
 
 // ---- own DMMA GEMM (bm_linalg.cuh): row-major C[m][n] = alpha * sum_k A(m,k) B(n,k) + beta * Cin[m][n] -------------
 // ak: A[m*lda + k] (else A[k*lda + m]);  bk: B[n*ldb + k] (else B[k*ldb + n]).  sym: C = A A^T, upper tiles mirrored.
-struct GemmBatch { int count = 1, bdiv = 1; long long sAhi = 0, sAlo = 0, sBhi = 0, sBlo = 0, sChi = 0, sClo = 0; };
+struct GemmBatch { int count = 1, bdiv = 1; long long sAhi = 0, sAlo = 0, sBhi = 0, sBlo = 0, sChi = 0, sClo = 0;
+                   const int* sel = nullptr; long long sAsel = 0, sBsel = 0; };
 int gemm(bm_ctx* c, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
          const double* B, long long ldb, double beta, const double* Cin, double* C, long long ldc, bool sym = false,
          const GemmBatch& gb = GemmBatch(), double* sumsq = nullptr) {
@@ -219,9 +222,10 @@ int gemm(bm_ctx* c, bool ak, bool bk, int M, int N, int K, double alpha, const d
   P.alpha = alpha; P.beta = beta; P.bdiv = gb.bdiv;
   P.sAhi = gb.sAhi; P.sAlo = gb.sAlo; P.sBhi = gb.sBhi; P.sBlo = gb.sBlo; P.sChi = gb.sChi; P.sClo = gb.sClo;
   P.sym = sym ? 1 : 0; P.sumsq = sumsq;
+  P.sel = gb.sel; P.sAsel = gb.sAsel; P.sBsel = gb.sBsel;
   auto even64 = [](long long v) { return (v & 1) == 0; };
   P.align16 = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && even64(lda) && even64(ldb) && even64(gb.sAhi) && even64(gb.sAlo) &&
-              even64(gb.sBhi) && even64(gb.sBlo);
+              even64(gb.sBhi) && even64(gb.sBlo) && even64(gb.sAsel) && even64(gb.sBsel);
   const int tm = (M + GM_T - 1) / GM_T, tn = (N + GM_T - 1) / GM_T;
   dim3 grid = sym ? dim3(tn * (tn + 1) / 2, 1, gb.count) : dim3(tn, tm, gb.count);
   if (ak && bk) k_dgemm<true, true><<<grid, GM_THREADS, 0, c->stream>>>(P);
@@ -589,7 +593,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->recE, c->recT, c->recV[0], c->recV[1], c->recU, c->recPix, c->recCount, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -1526,62 +1530,137 @@ int bm_sample(bm_ctx* c, int n, int rule, int start_site, const double* U_host, 
   return BM_OK;
 }
 
-// a11, general masks (TNutils.py:2053-2116): unknown pixels (255) anywhere in ONE image.
-int bm_reconstruct_one(bm_ctx* c, const uint8_t* pixels_host, const double* u_host, int n_unknown, uint8_t* out_host) {
+// a11 / f3, general masks (TNutils.py:2053-2116 `reconstruct`): unknown pixels (255) anywhere, B images sharing ONE
+// mask.  Exact conditionals: right pass E_j = sum_x M_j[x] E_{j+1} M_j[x]^T over the admissible x (batched DMMA GEMMs
+// with per-image operand selection; a vector while every site to the right is known), left pass one CTA per image.
+// u_host[b*n_unknown + i]: the uniform of image b for its i-th unknown pixel in site order (one np.random.rand() each).
+int bm_reconstruct_batch(bm_ctx* c, const uint8_t* pixels_host, int B, const double* u_host, int n_unknown, uint8_t* out_host) {
   if (!c) return BM_EINVAL;
-  REQUIRE(c->d == 2, "bm_reconstruct_one: binary pixels only");
-  REQUIRE(pixels_host && out_host && (n_unknown == 0 || u_host), "bm_reconstruct_one: bad arguments");
-  for (int j = 0; j < c->L; ++j) REQUIRE(c->sDl[j] > 0 && (j == c->L - 1 || c->sDr[j] == c->sDl[j + 1]), "bm_reconstruct_one: MPS not fully set");
+  REQUIRE(c->d == 2, "bm_reconstruct_batch: binary pixels only");
+  REQUIRE(pixels_host && out_host && B >= 1 && B <= 65535 && (n_unknown == 0 || u_host), "bm_reconstruct_batch: bad arguments");
+  for (int j = 0; j < c->L; ++j) REQUIRE(c->sDl[j] > 0 && (j == c->L - 1 || c->sDr[j] == c->sDl[j + 1]), "bm_reconstruct_batch: MPS not fully set");
   CU(cudaSetDevice(c->device));
-  const int L = c->L, D = c->Dcap;
-  const size_t esz = (size_t)D * D;
-  if (!c->recE) {
-    DALLOC(c->recE, esz * (L + 1)); DALLOC(c->recT, esz); DALLOC(c->recV[0], D); DALLOC(c->recV[1], D);
-    DALLOC(c->recU, L); DALLOC(c->recPix, L); DALLOC(c->recCount, 1);
+  const int L = c->L, D = c->Dcap, ldE = c->ldcap, ldv = c->ldcap;
+  const size_t esz = (size_t)D * ldE;
+  std::vector<int> rank_of(L, -1);
+  int cnt = 0, first_u = -1, last_u = -1;
+  for (int j = 0; j < L; ++j) {
+    const uint8_t p0 = pixels_host[j];
+    REQUIRE(p0 <= 1 || p0 == 255, "bm_reconstruct_batch: pixels must be 0, 1 or 255");
+    if (p0 == 255) { rank_of[j] = cnt++; if (first_u < 0) first_u = j; last_u = j; }
   }
-  int cnt = 0;
-  for (int j = 0; j < L; ++j) { REQUIRE(pixels_host[j] <= 1 || pixels_host[j] == 255, "bm_reconstruct_one: pixels must be 0, 1 or 255"); cnt += pixels_host[j] == 255; }
-  REQUIRE(cnt == n_unknown, "bm_reconstruct_one: number of uniforms must equal the number of unknown pixels");
-  CU(cudaMemcpyAsync(c->recPix, pixels_host, L, cudaMemcpyHostToDevice, c->stream));
-  if (n_unknown) CU(cudaMemcpyAsync(c->recU, u_host, (size_t)n_unknown * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemsetAsync(c->recCount, 0, sizeof(int), c->stream));
-  const double one = 1.0, zero = 0.0;
-  // ---- right pass: E_L = [1]; E_j = sum_x M_j[x] E_{j+1} M_j[x]^T  (row-major; cuBLAS sees the transposes)
-  CU(cudaMemcpyAsync(c->recE + esz * L, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  for (int j = L - 1; j >= 1; --j) {
-    const int Dl = c->sDl[j], Dr = c->sDr[j], ldr = even(Dr);
-    double* Ej = c->recE + esz * j;
-    const double* En = c->recE + esz * (j + 1);
-    bool first = true;
-    for (int x = 0; x < 2; ++x) {
-      const int pixel = 1 - x;                                   // physical index x <-> pixel 1-x
-      if (pixels_host[j] != 255 && pixels_host[j] != pixel) continue;
-      const double* M = c->Lf(j) + (size_t)x * ldr;              // row-major (Dl x Dr), ld = 2*ldr
-      // T = M E_{j+1}  (Dl x Dr): column-major view T^T (Dr x Dl) = E^T M^T = E M^T (E symmetric)
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_N, Dr, Dl, Dr, &one, En, D, M, 2 * ldr, &zero, c->recT, D));
-      // E_j (+)= T M^T (Dl x Dl): column-major view E_j^T = M T^T -> gemm(op_T on M view, N on T view)
-      LIB(cublasDgemm(c->cublas, CUBLAS_OP_T, CUBLAS_OP_N, Dl, Dl, Dr, &one, M, 2 * ldr, c->recT, D, first ? &zero : &one, Ej, D));
-      first = false;
+  REQUIRE(cnt == n_unknown, "bm_reconstruct_batch: number of uniforms per image must equal the number of unknown pixels");
+  for (int b = 1; b < B; ++b)
+    for (int j = 0; j < L; ++j) {
+      const uint8_t pb = pixels_host[(size_t)b * L + j];
+      REQUIRE(pb <= 1 || pb == 255, "bm_reconstruct_batch: pixels must be 0, 1 or 255");
+      REQUIRE((pb == 255) == (rank_of[j] >= 0), "bm_reconstruct_batch: all images of a batch must share one mask");
     }
-    k_rescale_matrix<<<1, 256, 0, c->stream>>>(Ej, Dl, D, nullptr);
+  if (n_unknown == 0) { std::memcpy(out_host, pixels_host, (size_t)B * L); return BM_OK; }
+  // ---- buffers (grow-only)
+  {
+    const size_t needE = (size_t)B * esz, needS = (size_t)n_unknown * needE;
+    if (needS > c->rbEst_cap || needE > c->rbE_cap) {
+      size_t fr = 0, tot = 0;
+      CU(cudaMemGetInfo(&fr, &tot));
+      const size_t have = fr + (c->rbEst_cap + 3 * c->rbE_cap) * sizeof(double);
+      const size_t want = (needS + 3 * needE) * sizeof(double);
+      if (want + (256u << 20) > have) {
+        const size_t per_img = ((size_t)n_unknown + 3) * esz * sizeof(double);
+        return fail(c, BM_ENOMEM, "bm_reconstruct_batch: " + std::to_string(B) + " images with " + std::to_string(n_unknown) +
+                    " unknown pixels need " + std::to_string(want >> 20) + " MiB of right-environment matrices; at most " +
+                    std::to_string(have > (256u << 20) ? (have - (256u << 20)) / per_img : 0) + " images fit");
+      }
+    }
+    if (needS > c->rbEst_cap) { DALLOC(c->rbEst, needS); c->rbEst_cap = needS; }
+    if (needE > c->rbE_cap) { DALLOC(c->rbEc[0], needE); DALLOC(c->rbEc[1], needE); DALLOC(c->rbT, needE); c->rbE_cap = needE; }
+    if ((size_t)B * ldv > c->rbV_cap) { DALLOC(c->rbV[0], (size_t)B * ldv); DALLOC(c->rbV[1], (size_t)B * ldv); c->rbV_cap = (size_t)B * ldv; }
+    if ((size_t)B * n_unknown > c->rbU_cap) { DALLOC(c->rbU, (size_t)B * n_unknown); c->rbU_cap = (size_t)B * n_unknown; }
+    if ((size_t)B * L > c->rbPix_cap) { DALLOC(c->rbPix, (size_t)B * L); DALLOC(c->rbSel, (size_t)B * L); c->rbPix_cap = (size_t)B * L; }
+  }
+  std::vector<int> sel((size_t)L * B, 0);               // physical index of the known pixel: x = 1 - pixel
+  for (int b = 0; b < B; ++b)
+    for (int j = 0; j < L; ++j) {
+      const uint8_t pb = pixels_host[(size_t)b * L + j];
+      sel[(size_t)j * B + b] = pb == 255 ? 0 : 1 - (int)pb;
+    }
+  CU(cudaMemcpyAsync(c->rbPix, pixels_host, (size_t)B * L, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->rbSel, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->rbU, u_host, (size_t)B * n_unknown * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  auto slot = [&](int site) { return c->rbEst + (size_t)rank_of[site] * B * esz; };
+  // ---- right pass: bonds j = L ... first_u + 1;  E_{j} is needed by the left pass iff site j-1 is unknown
+  {
+    std::vector<double> ones((size_t)B * ldv, 0.0);
+    for (int b = 0; b < B; ++b) ones[(size_t)b * ldv] = 1.0;
+    CU(cudaMemcpyAsync(c->rbV[0], ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));                 // `ones` and `sel` are stack/heap temporaries
+  }
+  bool rank1 = true;
+  int vcur = 0, pp = 0;
+  const double* curE = nullptr;                           // E_{j+1} when it is a matrix
+  if (rank_of[L - 1] >= 0) {                              // E_L = [1]
+    k_rec_outer<<<dim3(1, B), 256, 0, c->stream>>>(c->rbV[vcur], ldv, 1, slot(L - 1), ldE, (long long)esz);
     c->launches++;
   }
-  KCHECK();
-  // ---- left pass
-  int cur = 0;
-  CU(cudaMemcpyAsync(c->recV[0], &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  for (int j = 0; j < L; ++j) {
+  for (int j = L - 1; j > first_u; --j) {
     const int Dl = c->sDl[j], Dr = c->sDr[j], ldr = even(Dr);
-    size_t shm = (size_t)(2 * Dr + 16) * sizeof(double);
-    k_rec_site<<<1, 256, shm, c->stream>>>(c->Lf(j), Dl, Dr, ldr, c->recE + esz * (j + 1), D, c->recV[cur], c->recV[cur ^ 1],
-                                           c->recPix, j, c->recU, c->recCount);
+    const bool unk = rank_of[j] >= 0, out_needed = rank_of[j - 1] >= 0;
+    if (rank1 && !unk) {                                  // known suffix: r <- M_j[x_b] r
+      const size_t shm = (size_t)(Dr + Dl + 16) * sizeof(double);
+      k_rec_vec_left<<<B, 256, shm, c->stream>>>(c->Lf(j), Dl, Dr, ldr, c->rbV[vcur], c->rbV[vcur ^ 1], ldv, c->rbSel + (size_t)j * B);
+      c->launches++;
+      vcur ^= 1;
+      if (out_needed) {
+        k_rec_outer<<<dim3(std::max(1, std::min(64, (Dl * Dl + 255) / 256)), B), 256, 0, c->stream>>>(c->rbV[vcur], ldv, Dl, slot(j - 1), ldE, (long long)esz);
+        c->launches++;
+      }
+      continue;
+    }
+    const double* En = rank1 ? slot(j) : curE;            // rank1 && unknown: r r^T was materialised into slot(j)
+    double* out = out_needed ? slot(j - 1) : c->rbEc[pp];
+    if (!out_needed) pp ^= 1;
+    for (int x = 0; x < 2; ++x) {
+      if (!unk && x == 1) break;                          // known site: ONE product, operand chosen per image by sel
+      GemmBatch g1; g1.count = B; g1.sBhi = (long long)esz; g1.sChi = (long long)esz;
+      GemmBatch g2; g2.count = B; g2.sAhi = (long long)esz; g2.sChi = (long long)esz;
+      const double* M = c->Lf(j) + (unk ? (size_t)x * ldr : 0);
+      if (!unk) { g1.sel = c->rbSel + (size_t)j * B; g1.sAsel = ldr; g2.sel = g1.sel; g2.sBsel = ldr; }
+      // T_b = M E_b (Dl x Dr)
+      GEMM(true, false, Dl, Dr, Dr, 1.0, M, 2 * ldr, En, ldE, 0.0, nullptr, c->rbT, ldE, false, g1);
+      // E'_b (+)= T_b M^T (Dl x Dl)
+      GEMM(true, true, Dl, Dl, Dr, 1.0, c->rbT, ldE, M, 2 * ldr, x == 0 ? 0.0 : 1.0, x == 0 ? nullptr : out, out, ldE, false, g2);
+    }
+    k_rec_rescale_batch<<<B, 256, 0, c->stream>>>(out, Dl, ldE, (long long)esz, nullptr, 0);
+    c->launches++;
+    curE = out; rank1 = false;
+  }
+  KCHECK();
+  // ---- left pass (sites right of the last unknown pixel need no work: they are known)
+  {
+    std::vector<double> ones((size_t)B * ldv, 0.0);
+    for (int b = 0; b < B; ++b) ones[(size_t)b * ldv] = 1.0;
+    CU(cudaMemcpyAsync(c->rbV[0], ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  int cur = 0;
+  for (int j = 0; j <= last_u; ++j) {
+    const int Dl = c->sDl[j], Dr = c->sDr[j], ldr = even(Dr);
+    const size_t shm = (size_t)(Dl + 2 * Dr + 16) * sizeof(double);
+    const bool unk = rank_of[j] >= 0;
+    k_rec_site_batch<<<B, 256, shm, c->stream>>>(c->Lf(j), Dl, Dr, ldr, unk ? slot(j) : nullptr, ldE, (long long)esz,
+                                                 c->rbV[cur], c->rbV[cur ^ 1], ldv, c->rbPix, L, j, c->rbU, n_unknown, unk ? rank_of[j] : 0);
     c->launches++;
     cur ^= 1;
   }
   KCHECK();
-  CU(cudaMemcpyAsync(out_host, c->recPix, L, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out_host, c->rbPix, (size_t)B * L, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return BM_OK;
+}
+
+// one image: the batch of one (TNutils.py:2053-2116)
+int bm_reconstruct_one(bm_ctx* c, const uint8_t* pixels_host, const double* u_host, int n_unknown, uint8_t* out_host) {
+  return bm_reconstruct_batch(c, pixels_host, 1, u_host, n_unknown, out_host);
 }
 
 // ---- fused reduce + all-reduce over peer memory ----------------------------------------------------------------

@@ -1388,72 +1388,128 @@ __global__ void k_finish_logpsi(const double* __restrict__ E, int ld, const int*
 }
 
 // ------------------------------------------------------------------------------------------------
-// General-mask reconstruction of ONE image (reconstruct, TNutils.py:2053-2116).
-//   Right pass (host loop, cuBLAS): E_j = sum_{x allowed at site j} M_j[x] E_{j+1} M_j[x]^T, E_L = [1]   (Dl_j x Dl_j)
-//   Left pass (this kernel, one CTA per site, launched in site order): v <- v M_j[x] for known pixels; for unknown ones
-//   q_x = (v M_j[x]) E_{j+1} (v M_j[x])^T, P(pixel 0) = q_{phys 1} / (q_0 + q_1), accept pixel 0 iff u < P (the single-image
-//   rule of generate_sample, :1950/:1972/:1990), continue with the chosen branch.  v is rescaled by a power of two.
+// batched general-mask reconstruction (TNutils.py:2053-2116 for B images sharing one mask)
+//   right pass: E_j[b] = sum over the admissible x of M_j[x] E_{j+1}[b] M_j[x]^T  (k_dgemm, per-image operand selection)
+//               while every site to the right is known, E is the outer product of a vector: k_rec_vec_left carries it
+//   left pass:  k_rec_site_batch, one CTA per image
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rec_site(const double* __restrict__ Lf, int Dl, int Dr, int ldr,
-                                                  const double* __restrict__ Enext, int ldE,   // (Dr x Dr), row-major
-                                                  const double* __restrict__ vin, double* __restrict__ vout,
-                                                  uint8_t* __restrict__ pix, int site, const double* __restrict__ u, int* __restrict__ ucount) {
-  extern __shared__ double shm[];          // w0[Dr], w1[Dr], red[...]
-  double* w0 = shm; double* w1 = shm + Dr; double* red = shm + 2 * Dr;
+// r_out[b][a] = sum_n M_j[x_b][a][n] r_in[b][n], rescaled by a power of two.  One CTA per image.
+__global__ void __launch_bounds__(256) k_rec_vec_left(const double* __restrict__ Lf, int Dl, int Dr, int ldr,
+                                                      const double* __restrict__ rin, double* __restrict__ rout, int ldv,
+                                                      const int* __restrict__ xsel) {
+  extern __shared__ double shm[];          // rin[Dr], out[Dl], red[16]
+  double* rs = shm; double* os = shm + Dr; double* red = shm + Dr + Dl;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int n = tid; n < Dr; n += 256) rs[n] = rin[(long long)b * ldv + n];
+  __syncthreads();
+  const double* M = Lf + (long long)xsel[b] * ldr;          // M[a][n] = Lf[(a*2 + x)*ldr + n]
+  double m = 0.0;
+  for (int a = warp; a < Dl; a += 8) {
+    const double* row = M + (long long)a * 2 * ldr;
+    double s = 0.0;
+    for (int n = lane; n < Dr; n += 32) s = fma(row[n], rs[n], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) os[a] = s;
+    m = fmax(m, fabs(s));
+  }
+  const double mx = block_max(m, red);
+  __shared__ double scale;
+  if (tid == 0) scale = mx > 0.0 ? pow2d(-frexp_exp(mx)) : 1.0;
+  __syncthreads();
+  for (int a = tid; a < Dl; a += 256) rout[(long long)b * ldv + a] = os[a] * scale;
+}
+
+// E[b] = r[b] r[b]^T  (n x n, row-major ld)
+__global__ void __launch_bounds__(256) k_rec_outer(const double* __restrict__ r, int ldv, int n, double* __restrict__ E, int ld,
+                                                   long long estride) {
+  const int b = blockIdx.y;
+  const double* rb = r + (long long)b * ldv;
+  double* Eb = E + (long long)b * estride;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)n * n; i += (long long)gridDim.x * 256) {
+    const int row = (int)(i / n), col = (int)(i % n);
+    Eb[(long long)row * ld + col] = rb[row] * rb[col];
+  }
+}
+
+// E[b] (n x n) /= 2^e, e = exponent of max|E[b]|; optionally a copy into the slot the left pass reads.  One CTA per image.
+__global__ void __launch_bounds__(256) k_rec_rescale_batch(double* __restrict__ E, int n, int ld, long long estride,
+                                                           double* __restrict__ copy, long long cstride) {
+  __shared__ double red[8];
+  __shared__ double sc;
+  double* Eb = E + (long long)blockIdx.x * estride;
+  double m = 0.0;
+  for (long long i = threadIdx.x; i < (long long)n * n; i += 256) m = fmax(m, fabs(Eb[(i / n) * ld + (i % n)]));
+  const double mx = block_max(m, red);
+  if (threadIdx.x == 0) sc = mx > 0.0 ? pow2d(-frexp_exp(mx)) : 1.0;
+  __syncthreads();
+  double* Cb = copy ? copy + (long long)blockIdx.x * cstride : nullptr;
+  for (long long i = threadIdx.x; i < (long long)n * n; i += 256) {
+    const long long off = (i / n) * ld + (i % n);
+    const double v = Eb[off] * sc;
+    Eb[off] = v;
+    if (Cb) Cb[off] = v;
+  }
+}
+
+// left pass, one site, one CTA per image:  w_x = v M_j[x];  known pixel -> v <- w_{1-pixel};  unknown pixel ->
+// q_x = w_x^T E_{j+1} w_x,  P(pixel 0) = q_1 / (q_0 + q_1)  (pixel 0 <-> physical index 1),  pixel 0 iff u < P.
+__global__ void __launch_bounds__(256) k_rec_site_batch(const double* __restrict__ Lf, int Dl, int Dr, int ldr,
+                                                        const double* __restrict__ Enext, int ldE, long long estride,
+                                                        const double* __restrict__ vin, double* __restrict__ vout, int ldv,
+                                                        uint8_t* __restrict__ pix, int L, int site,
+                                                        const double* __restrict__ u, int n_unknown, int uidx) {
+  extern __shared__ double shm[];          // v[Dl], w0[Dr], w1[Dr], red[16]
+  double* vs = shm; double* w0 = shm + Dl; double* w1 = w0 + Dr; double* red = w1 + Dr;
   __shared__ int choice;
-  const int tid = threadIdx.x;
-  const int known = pix[site];             // pixel value 0/1, 255 = unknown
-  // w_x[b] = sum_a v[a] * M[a][x][b]   (L-form: Lf[(a*2 + x)*ldr + b])
-  for (int b = tid; b < Dr; b += 256) {
+  __shared__ double qacc[2][8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int known = pix[(long long)b * L + site];
+  for (int a = tid; a < Dl; a += 256) vs[a] = vin[(long long)b * ldv + a];
+  __syncthreads();
+  for (int n = tid; n < Dr; n += 256) {
     double s0 = 0.0, s1 = 0.0;
     for (int a = 0; a < Dl; ++a) {
-      double va = vin[a];
-      s0 = fma(va, Lf[((long long)a * 2 + 0) * ldr + b], s0);
-      s1 = fma(va, Lf[((long long)a * 2 + 1) * ldr + b], s1);
+      const double va = vs[a];
+      s0 = fma(va, Lf[((long long)a * 2 + 0) * ldr + n], s0);
+      s1 = fma(va, Lf[((long long)a * 2 + 1) * ldr + n], s1);
     }
-    w0[b] = s0; w1[b] = s1;
+    w0[n] = s0; w1[n] = s1;
   }
   __syncthreads();
   if (known == 255) {
-    // q_x = w_x^T E w_x
+    const double* Eb = Enext + (long long)b * estride;
     double q0 = 0.0, q1 = 0.0;
-    for (int r = tid; r < Dr; r += 256) {
+    for (int r = warp; r < Dr; r += 8) {                 // a warp per row of E: coalesced reads
+      const double* er = Eb + (long long)r * ldE;
       double t0 = 0.0, t1 = 0.0;
-      const double* er = Enext + (long long)r * ldE;
-      for (int c = 0; c < Dr; ++c) { double e = er[c]; t0 = fma(e, w0[c], t0); t1 = fma(e, w1[c], t1); }
+      for (int cidx = lane; cidx < Dr; cidx += 32) { const double e = er[cidx]; t0 = fma(e, w0[cidx], t0); t1 = fma(e, w1[cidx], t1); }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
       q0 = fma(w0[r], t0, q0); q1 = fma(w1[r], t1, q1);
     }
-    double a0 = block_sum(q0, red), a1 = block_sum(q1, red);
+    if (lane == 0) { qacc[0][warp] = q0; qacc[1][warp] = q1; }
+    __syncthreads();
     if (tid == 0) {
-      int k = atomicAdd(ucount, 1);
-      double p_pixel0 = a1 / (a0 + a1);              // pixel 0 <-> physical index 1
-      int pixel = (u[k] < p_pixel0) ? 0 : 1;
-      pix[site] = (uint8_t)pixel;
-      choice = 1 - pixel;                            // physical index of the chosen branch
+      double a0 = 0.0, a1 = 0.0;
+      for (int w = 0; w < 8; ++w) { a0 += qacc[0][w]; a1 += qacc[1][w]; }
+      const double p_pixel0 = a1 / (a0 + a1);
+      const int pixel = (u[(long long)b * n_unknown + uidx] < p_pixel0) ? 0 : 1;
+      pix[(long long)b * L + site] = (uint8_t)pixel;
+      choice = 1 - pixel;
     }
   } else if (tid == 0) choice = 1 - known;
   __syncthreads();
   const double* w = choice == 0 ? w0 : w1;
   double m = 0.0;
-  for (int b = tid; b < Dr; b += 256) m = fmax(m, fabs(w[b]));
-  double mx = block_max(m, red);
+  for (int n = tid; n < Dr; n += 256) m = fmax(m, fabs(w[n]));
+  const double mx = block_max(m, red);
   __shared__ double scale;
-  if (tid == 0) scale = pow2d(-frexp_exp(mx));
+  if (tid == 0) scale = mx > 0.0 ? pow2d(-frexp_exp(mx)) : 1.0;
   __syncthreads();
-  for (int b = tid; b < Dr; b += 256) vout[b] = w[b] * scale;
+  for (int n = tid; n < Dr; n += 256) vout[(long long)b * ldv + n] = w[n] * scale;
 }
 
-// E (n x n, row-major ld) /= 2^e with e = exponent of max|E|  (keeps the right-environment chain in range)
-__global__ void __launch_bounds__(256) k_rescale_matrix(double* __restrict__ E, int n, int ld, double* __restrict__ scratch) {
-  __shared__ double red[8];
-  __shared__ double sc;
-  double m = 0.0;
-  for (long long i = threadIdx.x; i < (long long)n * n; i += 256) m = fmax(m, fabs(E[(i / n) * ld + (i % n)]));
-  double mx = block_max(m, red);
-  if (threadIdx.x == 0) sc = pow2d(-frexp_exp(mx));
-  __syncthreads();
-  for (long long i = threadIdx.x; i < (long long)n * n; i += 256) E[(i / n) * ld + (i % n)] *= sc;
-}
 
 // counter-based uniforms in [0,1): splitmix64(seed, site, sample) >> 11 * 2^-53
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

@@ -34,6 +34,8 @@ struct GemmParams {
   int sym;                           // 1: C symmetric (A == B, M == N): only tiles bn >= bm are computed, mirrored on store
   int align16;                       // every tile-row start of A and B is 16-byte aligned
   double* sumsq;                     // optional: per-CTA sum of squares of the stored outputs -> sumsq[linear CTA index]
+  const int* sel;                    // optional per-batch operand selector: A += sel[z]*sAsel, B += sel[z]*sBsel
+  long long sAsel, sBsel;            //   (batched reconstruction: the site matrix of image z's known pixel)
 };
 
 template <bool KMAJOR>
@@ -86,8 +88,9 @@ __global__ void __launch_bounds__(GM_THREADS) k_dgemm(GemmParams P) {
   } else { bm_ = blockIdx.y; bn_ = blockIdx.x; }
   const int m0 = bm_ * GM_T, n0 = bn_ * GM_T;
   const int zh = blockIdx.z / P.bdiv, zl = blockIdx.z % P.bdiv;
-  const double* __restrict__ A = P.A + zh * P.sAhi + zl * P.sAlo;
-  const double* __restrict__ B = P.B + zh * P.sBhi + zl * P.sBlo;
+  const int sidx = P.sel ? P.sel[blockIdx.z] : 0;
+  const double* __restrict__ A = P.A + zh * P.sAhi + zl * P.sAlo + sidx * P.sAsel;
+  const double* __restrict__ B = P.B + zh * P.sBhi + zl * P.sBlo + sidx * P.sBsel;
   const long long coff = zh * P.sChi + zl * P.sClo;
   double acc[2][2][2];
 #pragma unroll

@@ -398,6 +398,32 @@ class BornEngine:
         check(self._ctx, self._lib.bm_reconstruct_one(self._ctx, _ptr(px), _ptr(uu) if uu.size else None, int(uu.size), _ptr(out)))
         return out
 
+    def reconstruct_batch(self, imgs, U, max_images=None):
+        """`reconstruct` (TNutils.py:2053-2116) for a batch of images sharing one mask: imgs (B,L) with -1/255 for unknown
+        pixels, U (B, n_unknown) uniforms (image b's draws in site order).  Returns (B,L) uint8.  The batch is split so
+        that the right-environment matrices of a chunk (chunk * n_unknown * Dcap^2 * 8 bytes) fit in free memory."""
+        a = np.asarray(imgs)
+        if a.ndim != 2 or a.shape[1] != self.L:
+            raise ValueError(f'expected (B,{self.L}) images')
+        px = np.ascontiguousarray(np.where(a < 0, 255, a).astype(np.uint8))
+        B = px.shape[0]
+        unk = px[0] == 255
+        if not np.array_equal(px == 255, np.broadcast_to(unk, px.shape)):
+            raise ValueError('all images of a batch must share one mask (group them by mask first)')
+        nu = int(unk.sum())
+        uu = np.ascontiguousarray(np.asarray(U, dtype=np.float64).reshape(B, nu))
+        out = np.empty((B, self.L), dtype=np.uint8)
+        if max_images is None:
+            free, _ = torch.cuda.mem_get_info(self.device)
+            ld = (self.Dcap + 1) & ~1
+            per = (nu + 3) * self.Dcap * ld * 8
+            max_images = int(max(1, min(B, (free * 0.8) // max(per, 1))))
+        for lo in range(0, B, max_images):
+            hi = min(B, lo + max_images)
+            check(self._ctx, self._lib.bm_reconstruct_batch(self._ctx, _ptr(px[lo:hi]), hi - lo, _ptr(uu[lo:hi]) if nu else None,
+                                                            nu, _ptr(out[lo:hi])))
+        return out
+
     def sample_device_ms(self, n, seed=0, rule='batched'):
         ms = C.c_float()
         check(self._ctx, self._lib.bm_sample_device(self._ctx, n, RULE[rule], C.c_uint64(seed), C.byref(ms)))

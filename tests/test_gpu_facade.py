@@ -225,3 +225,22 @@ def test_no_max_bond_lets_the_bond_grow(T):
     cache2 = T.left_right_cache(mps2, data)
     tn = T.learning_step_cached(mps2, 5, data, 0.05, cache2, True)
     assert tn.tensors[0].data.shape[-1] == tn.info['chi'] > 2
+
+
+def test_reconstruct_batch_equals_the_per_image_loop(T):
+    """facade extension reconstruct_batch == [reconstruct(mps, img) for img in imgs] under the same np.random seed
+    (same draws in the same order, TNutils.py:2053-2116), for mixed masks (prefix, general) in one call."""
+    np.random.seed(21)
+    mps = T.initialize_mps(36, 5)
+    rng = np.random.default_rng(22)
+    imgs = (rng.random((9, 36)) < 0.4).astype(int)
+    corr = []
+    for i, img in enumerate(imgs):
+        corr.append(T.partial_removal_img(img, (6, 6), .5, i % 2, (i // 2) % 2))
+    corr = np.array(corr)
+    np.random.seed(5)
+    want = np.array([T.reconstruct(mps, c) for c in corr])
+    np.random.seed(5)
+    got = T.reconstruct_batch(mps, corr)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[corr != -1], corr[corr != -1]) and set(np.unique(got)) <= {0, 1}
