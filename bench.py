@@ -335,7 +335,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     clk = clocks.stop() if (rank == 0 and full) else {}
     value = N * steps / (dev_ms * 1e-3)
     rec = {'value': value, 'ms_per_step': dev_ms / steps, 'step_ms': step_ms, 'gram_levels': levels, 'chi': int(chis[-1]),
-           'gpu_launches': int(launches), 'split_eig': {'on_chip': eig1[0] - eig0[0], 'cusolver_fallback': eig1[1] - eig0[1]},
+           'gpu_launches': int(launches), 'split_eig': {'on_chip': eig1[0] - eig0[0], 'cusolver_fallback': eig1[1] - eig0[1], 'fallback_reasons_since_setup': eng.eig_fallback_reasons()},
            'wall_s_timed': wall, 'setup_s': t_setup, 'allreduce': allreduce_mode, 'clocks': clk, 'N': N, 'L': L, 'D': D, 'd': d}
     if not full:
         eng.set_timing(True)
@@ -481,6 +481,10 @@ def run_ours(args):
             others['c4'] = sampler_record(args, rank, world, local, n_samples=100000, steps=1)
         except Exception as exc:
             others['c4'] = {'error': str(exc)}
+        try:
+            others['c4_reconstruct'] = reconstruct_record(args, local)
+        except Exception as exc:
+            others['c4_reconstruct'] = {'error': str(exc)}
 
     if rank == 0:
         cpu = None
@@ -582,6 +586,45 @@ def sampler_record(args, rank, world, local, n_samples, steps):
                 'cpu_baseline': {'value': nc / tc, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port', 'blas_threads': blas_threads(),
                                  'sample': f'8 mid-chain sites at D={D} on {nc} samples (numpy float64 port of generate_samples), x{L}/8'}}
     return line
+
+
+def reconstruct_record(args, local, n_prefix=20000, n_general=64):
+    """Config 4, second half: half-image reconstruction (reconstruct, TNutils.py:2053-2116 on
+    partial_removal_img(img, (28,28), .5, axis=0, half) masks) at D = --sampler-bond.
+      half=0 (bottom half unknown): known prefix -> batched sampler path, n_prefix images in one call;
+      half=1 (top half unknown): general mask -> bm_reconstruct_batch (D^3 per site and image: right-environment
+      matrices), n_general images in one call.  Host pixels + host uniforms in, host pixels out (e2e by construction)."""
+    import torch
+    from mps_born_machines_b200 import BornEngine, mpslib
+    L, D = 784, args.sampler_bond
+    mps = mpslib.random_mps(L, D, rng=np.random.default_rng(13), centre=0)
+    eng = BornEngine(L, D, device=local)
+    eng.set_mps(mps)
+    rng = np.random.default_rng(19)
+    out = {}
+    imgs = mpslib.synthetic_images(n_prefix, L)
+    corr = imgs.copy(); corr[:, 392:] = -1
+    U = rng.random((392, n_prefix))
+    eng.sample(256, U=U[:, :256].copy(), rule='single', prefix=corr[:256], start_site=392)        # warm-up
+    torch.cuda.synchronize(); l0 = eng.launch_count(); t0 = time.perf_counter()
+    got = eng.sample(n_prefix, U=U, rule='single', prefix=corr, start_site=392)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(got[:, :392], imgs[:, :392].astype(np.uint8))
+    out['bottom_half_unknown'] = {'images': n_prefix, 'seconds': dt, 'images_per_s': n_prefix / dt, 'gpu_launches': eng.launch_count() - l0,
+                                  'path': 'known prefix: prefix chain + batched single-rule sampler (bm_sample)'}
+    corr = imgs[:n_general].copy(); corr[:, :392] = -1
+    U2 = rng.random((n_general, 392))
+    eng.reconstruct_batch(corr[:2], U2[:2])                                                        # warm-up
+    torch.cuda.synchronize(); l0 = eng.launch_count(); t0 = time.perf_counter()
+    got = eng.reconstruct_batch(corr, U2)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(got[:, 392:], imgs[:n_general, 392:].astype(np.uint8))
+    flops = n_general * 391 * 4 * 2.0 * D ** 3
+    out['top_half_unknown'] = {'images': n_general, 'seconds': dt, 'images_per_s': n_general / dt, 'gpu_launches': eng.launch_count() - l0,
+                               'tflops': flops / dt / 1e12,
+                               'path': 'general mask: batched right-environment matrices (bm_reconstruct_batch), 4 D^3 products per unknown site and image'}
+    eng.close()
+    return out
 
 
 def run_sampler(args):

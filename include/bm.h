@@ -61,6 +61,10 @@ int bm_eig_sym(bm_ctx* ctx, int n, const double* G_host, int m, int on_chip, dou
 /* how many splits ran on the on-chip eigensolver / fell back to cuSOLVER (degenerate spectra, n > 512), and the
  * number of deflation levels the last Gram split needed (may be NULL) */
 int bm_eig_stats(bm_ctx* ctx, long long* on_chip, long long* fallback, int* last_levels);
+/* why splits left the on-chip path, counts since bm_create: [0] cluster launch refused, [1] non-finite eigenvalues,
+ * [2] zero matrix, [3] more than 8 deflation levels, [4] kept values unresolved at the last level, [5] kept eigenvalues
+ * numerically degenerate (closer than 1e-14 of the largest), [6] orthonormality check failed after the polish, [7] unused */
+int bm_eig_fallback_reasons(bm_ctx* ctx, long long* out8);
 /* grad_tf32 = 1: accumulate S = sum psi'/psi with tcgen05.mma.kind::tf32 into TMEM (1e-3 parity class; bonds <= 256,
  * larger bonds fall back to the FP64 DMMA kernel).  psi, environments, update and split stay FP64. */
 int bm_set_precision(bm_ctx* ctx, int grad_tf32);

@@ -21,6 +21,7 @@ _SIGS = [
     ('bm_set_svd', C.c_int, [_P, C.c_int]),
     ('bm_eig_sym', C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]),
     ('bm_eig_stats', C.c_int, [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    ('bm_eig_fallback_reasons', C.c_int, [_P, _P]),
     ('bm_set_precision', C.c_int, [_P, C.c_int]),
     ('bm_set_data', C.c_int, [_P, _P, C.c_int]),
     ('bm_set_site', C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int]),

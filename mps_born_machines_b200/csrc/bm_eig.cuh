@@ -4,9 +4,9 @@
 // cuSOLVER `syevd` (5.3 ms at 512x512: ~8 us per column of launch-bound tridiagonalisation).  This file keeps the whole
 // factorisation on chip:
 //   k_sytrd_cluster   Householder tridiagonalisation inside ONE thread-block cluster of 16 CTAs.  The symmetric matrix
-//                     lives in registers (CTA i holds rows i, i+16, ...; thread t holds column t of those 32 rows), the
-//                     per-column exchanges (norm, v, A.v) go through distributed shared memory and hardware cluster
-//                     barriers (3 per column) instead of kernel launches.
+//                     lives in registers (CTA i holds rows i, i+16, ...; thread (g, cg) an 8 x 4 block of them), ONE
+//                     exchange per column through distributed shared memory (bulk copies + mbarrier transaction
+//                     counts) instead of kernel launches.
 //   k_tri_eigvals     all eigenvalues of the tridiagonal matrix by 33-section with Sturm counts, one warp per
 //                     eigenvalue (division-free three-term recurrence, power-of-two rescaling).
 //   k_tri_vectors     eigenvectors of selected eigenvalues by twisted factorisation (one forward and one backward
@@ -104,16 +104,27 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity)
 // the not-yet-updated column j+1 and its partial p.v to all CTAs as ONE 528-byte bulk copy per destination
 // (cp.async.bulk shared::cta -> shared::cluster); the receivers wait on a local mbarrier (transaction bytes),
 // double-buffered by the parity of j.
+//
+// Schedule of one column (round 2, driven by phase clocks -- profiles/r02_sytrd_phases.md; the kernel is bound by the
+// shared-memory/shuffle queue and by warp 0's serial chain, not by FP64 throughput or the exchange flight time):
+//   B   every warp: q = A xh on its register block, transpose-reduce, partial row sums -> part;  its 8 entries of
+//       column j+1 -> cslice                                                                        [CTA barrier]
+//   C   warp 0: p, p.v, message -> sbuf, fence.proxy.async, expect_tx                               [CTA barrier]
+//       warp w: ONE bulk copy to CTA w (16 copies issued by the lanes of one warp serialise: 1000 cycles);
+//       everybody: v -> vfull, reflector store; wait for the 16 incoming messages
+//   D   every thread: p.v tree, w, element t of the next column -> wfull, xfull                     [CTA barrier]
+//   U   warps 1..15: rank-2 update of the register block.  Warp 0 FIRST computes the norm and the Householder scalars
+//       of the NEXT column from xfull (one butterfly; while the other warps are in their FP64-bound update the queue
+//       is free -- in phase B the same chain took 1900 cycles behind the other warps' shuffles), then its update.
 constexpr int SYTRD_MSG = 2 * EIG_LR + 2;                     // p[32], column slice[32], p.v, pad -> 528 bytes
 constexpr uint32_t SYTRD_TX_BYTES = EIG_CL * SYTRD_MSG * 8;
-template <bool ONE_POLLER>
+template <bool PROF>
 __global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_NT, 1)
 k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict__ d, double* __restrict__ e,
-                double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status) {
+                double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status, long long* __restrict__ prof) {
   __shared__ __align__(16) double vfull[EIG_NMAX], wfull[EIG_NMAX];
   __shared__ __align__(16) double rbuf[2][EIG_CL][SYTRD_MSG];   // received messages, one per source CTA
   __shared__ __align__(16) double sbuf[2][SYTRD_MSG];           // my outgoing message
-  __shared__ double nrm[EIG_NT / 32];
   __shared__ double part[EIG_NT / 32][8];
   __shared__ double cslice[EIG_LR];
   __shared__ double scl[4];
@@ -134,45 +145,60 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
     }
   }
   double x = t < n ? G[t] : 0.0;                  // full column 0
+  xfull[t] = t > 0 ? x : 0.0;
   if (t == 0) {
+    if (me == 0) d[0] = x;
     mbar_init(eig_smem_u32(&bars[0]), 1);
     mbar_init(eig_smem_u32(&bars[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // norm and Householder scalars of column jc from xfull (xfull[r] = 0 for r <= jc): warp 0 only, one butterfly.
+  // Lane l sums the entries 2l + 64k, 2l + 64k + 1 (16-byte reads, conflict-free), in a fixed order: bit-identical in
+  // every CTA of the cluster.
+  auto scalars_for = [&](int jc) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const int e0 = 2 * lane + 64 * k, e1 = e0 + 64;
+      const double2 u = *reinterpret_cast<const double2*>(&xfull[e0]);
+      const double2 w2 = *reinterpret_cast<const double2*>(&xfull[e1]);
+      s0 = fma(e0 == jc + 1 ? 0.0 : u.x, u.x, s0);            // the entry jc+1 is alpha, not part of the norm
+      s1 = fma(e0 + 1 == jc + 1 ? 0.0 : u.y, u.y, s1);
+      s2 = fma(e1 == jc + 1 ? 0.0 : w2.x, w2.x, s2);
+      s3 = fma(e1 + 1 == jc + 1 ? 0.0 : w2.y, w2.y, s3);
+    }
+    const double xn2 = warp_sum((s0 + s1) + (s2 + s3));
+    const double alpha = xfull[jc + 1];
+    double beta = alpha, tj = 0.0, scale = 0.0;
+    if (xn2 != 0.0) {
+      const double nn = fma(alpha, alpha, xn2);
+      const double rinv = fast_rsqrt(nn);                     // 1/|beta|
+      beta = -copysign(nn * rinv, alpha);
+      tj = (beta - alpha) * (-copysign(rinv, alpha));          // (beta - alpha) / beta
+      scale = fast_rcp(alpha - beta);
+    }
+    if (lane == 0) { scl[0] = beta; scl[1] = tj; scl[2] = scale; }
+  };
+  if (warp == 0 && n > 2) scalars_for(0);
+  __syncthreads();
   cluster_sync_all();                             // every CTA resident, barriers initialised
   bool ok = true;
+  // PROF: lane 0 of warps 0, 1 and 15 of CTA 0 accumulate the cycles between the marks (phase clocks)
+  const bool pr = PROF && prof != nullptr && me == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 15);
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+#define SYC_MARK(i) do { if (PROF && pr) { const long long now_ = clock64(); ph[i] += now_ - tc; tc = now_; } } while (0)
+  if (pr) tc = clock64();
   for (int j = 0; j + 2 < n; ++j) {
     const int par = j & 1;
-    // ---- A: publish the masked column xh (xh[t] = x[t] for t > j, else 0), partial norms, my part of column j+1
-    xfull[t] = (t > j) ? x : 0.0;
-    {
-      const double s = warp_sum((t > j + 1) ? x * x : 0.0);
-      if (lane == 0) nrm[warp] = s;
-      if (t == j && me == 0) d[j] = x;
-    }
-    if (cg == ((j + 1) >> 2)) {                   // my 8 entries of the not-yet-updated column j+1
+    // ---- B: my 8 entries of the not-yet-updated column j+1;  q = A xh on my rows (does not need the scalars:
+    //         A v = scale (A xh - beta A[:, j+1]))
+    if (cg == ((j + 1) >> 2)) {
       const int kk = (j + 1) & 3;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         cslice[8 * g + i] = kk == 0 ? a[i][0] : (kk == 1 ? a[i][1] : (kk == 2 ? a[i][2] : a[i][3]));
     }
-    __syncthreads();
-    // Householder scalars: ONE warp (the others would only repeat them), interleaved with its share of the product
-    if (warp == 0) {
-      const double xn2 = warp_sum(lane < EIG_NT / 32 ? nrm[lane] : 0.0);
-      const double alpha = xfull[j + 1];
-      double beta = alpha, tj = 0.0, scale = 0.0;
-      if (xn2 != 0.0) {
-        const double nn = fma(alpha, alpha, xn2);
-        const double rinv = fast_rsqrt(nn);                     // 1/|beta|
-        beta = -copysign(nn * rinv, alpha);
-        tj = (beta - alpha) * (-copysign(rinv, alpha));          // (beta - alpha) / beta
-        scale = fast_rcp(alpha - beta);
-      }
-      if (lane == 0) { scl[0] = beta; scl[1] = tj; scl[2] = scale; }
-    }
-    // ---- B: q = A xh on my rows (does not need the scalars:  A v = scale (A xh - beta A[:, j+1]))
     // A warp's 64 x 128 tile is dead once all its columns or all its rows are <= j (the trailing block shrinks):
     // dead tiles contribute zeros and are skipped, in the product and in the update (a third of the work on average).
     const bool live = (128 * (warp & 3) + 127 > j) && (me + EIG_CL * (8 * g + 7) > j);
@@ -203,8 +229,11 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
       if ((lane & 3) == 0) part[warp][(((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1)] = q[0];
     }
+    SYC_MARK(0);                                   // B: slice, q = A xh, transpose-reduce
     __syncthreads();
+    SYC_MARK(1);                                   // barrier
     const double beta = scl[0], tj = scl[1], scale = scl[2];
+    // ---- C: warp 0 forms p on my rows, the partial p.v and the message
     if (warp == 0) {
       const int r = me + EIG_CL * lane;
       const int gl = lane >> 3, il = lane & 7;
@@ -215,12 +244,8 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       sbuf[par][lane] = p;
       sbuf[par][EIG_LR + lane] = cslice[lane];
       if (lane == 0) sbuf[par][2 * EIG_LR] = dp;
-      fence_proxy_async_smem();
-      __syncwarp();
+      fence_proxy_async_smem();                    // my generic-proxy writes precede the bulk copies issued after the barrier
       if (lane == 0) mbar_expect_tx(eig_smem_u32(&bars[par]), SYTRD_TX_BYTES);
-      if (lane < EIG_CL)
-        bulk_copy_to_cta(mapa_u32(eig_smem_u32(&rbuf[par][me][0]), lane), eig_smem_u32(&sbuf[par][0]), SYTRD_MSG * 8,
-                         mapa_u32(eig_smem_u32(&bars[par]), lane));
     }
     const double vt = (t > j + 1) ? x * scale : (t == j + 1 ? 1.0 : 0.0);
     vfull[t] = vt;
@@ -228,15 +253,15 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       V[(size_t)j * EIG_LDV + t] = vt;
       if (t == 0) { e[j] = beta; tau[j] = tj; }
     }
-    // ONE_POLLER: only warp 0 polls the mbarrier, the other warps sleep at the hardware CTA barrier (15 polling warps
-    // congest the shared-memory/shuffle queue that warp 0's send path needs: ncu + phase clocks, r02_sytrd_phases.log)
-    if (ONE_POLLER) {
-      if (warp == 0) ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
-      __syncthreads();
-    } else {
-      ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
-    }
-    // ---- D: w, the next full column, rank-2 update of my block
+    SYC_MARK(2);                                   // C: (warp 0: p, p.v, message) v, reflector store
+    __syncthreads();                               // message complete
+    if (lane == 0)
+      bulk_copy_to_cta(mapa_u32(eig_smem_u32(&rbuf[par][me][0]), warp), eig_smem_u32(&sbuf[par][0]), SYTRD_MSG * 8,
+                       mapa_u32(eig_smem_u32(&bars[par]), warp));
+    SYC_MARK(3);                                   // barrier + my bulk copy issued
+    ok = mbar_wait_cluster(eig_smem_u32(&bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
+    SYC_MARK(4);                                   // exchange wait
+    // ---- D: w, element t of the next full column
     double dsum[EIG_CL];
 #pragma unroll
     for (int c = 0; c < EIG_CL; ++c) dsum[c] = rbuf[par][c][2 * EIG_LR];
@@ -250,7 +275,13 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
     const double wj1 = rbuf[par][(j + 1) & 15][(j + 1) >> 4] + al2;   // v[j+1] = 1
     wfull[t] = wt;
     x = rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);      // column j+1 of A - v w^T - w v^T
+    xfull[t] = (t > j + 1) ? x : 0.0;                                 // published for the next column
+    if (me == 0 && t == j + 1) d[j + 1] = x;
+    SYC_MARK(5);                                   // D: dot tree, w, next column
     __syncthreads();
+    SYC_MARK(6);                                   // barrier
+    // ---- U: (warp 0: norm + scalars of the next column first) rank-2 update of my block
+    if (warp == 0 && j + 3 < n) scalars_for(j + 1);
     if (live && 4 * cg + 3 > j) {
       const double2 v01 = *reinterpret_cast<const double2*>(&vfull[4 * cg]);
       const double2 v23 = *reinterpret_cast<const double2*>(&vfull[4 * cg + 2]);
@@ -267,265 +298,18 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
         a[i][3] = fma(nvs, w23.y, fma(nws, v23.y, a[i][3]));
       }
     }
+    SYC_MARK(7);                                   // U: (scalars) + rank-2 update
   }
-  // trailing entries: x is the full column n-2 (n >= 2) or column 0 (n == 1)
-  if (me == 0) {
-    if (n >= 2) {
-      if (t == n - 2) d[n - 2] = x;
-      if (t == n - 1) e[n - 2] = x;
-    } else if (t == 0) d[0] = x;
-  }
+  if (PROF && pr) for (int i = 0; i < 8; ++i) prof[(warp == 0 ? 0 : (warp == 1 ? 8 : 16)) + i] = ph[i];
+#undef SYC_MARK
+  // trailing entries: x is the full column n-2 (n >= 2) or column 0 (n == 1); d[n-2] was stored in phase D (or above)
+  if (me == 0 && n >= 2 && t == n - 1) e[n - 2] = x;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = me + EIG_CL * (8 * g + i);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (n >= 2 && r == n - 1 && 4 * cg + k == n - 1) d[n - 1] = a[i][k];
-  }
-  if (!ok && t == 0) atomicExch(status, 3);
-  cluster_sync_all();                             // nobody exits while a peer could still address its shared memory
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// k_sytrd_fused — second generation of the tridiagonalisation: same arithmetic, outputs, distribution over the 16-CTA
-// cluster and exchange mechanism (one bulk copy per destination, mbarrier transaction count) as k_sytrd_cluster, with
-// the per-column critical path restructured around what ncu showed (profiles/r01_ncu_eig_kernels.md):
-//  * thread layout 2 rows x 16 columns (warp w: local rows 2w, 2w+1; lane l: columns 2l+64i, 2l+64i+1): a row's inner
-//    product lives in ONE warp (5 shuffle rounds, the first one transposing the two rows onto the two half-warps), no
-//    cross-warp partial sums;
-//  * the rank-2 update of column j-1 and the product with column j are ONE pass over the registers;
-//  * the squared norm of column j+1 is reduced while that column is formed and the Householder scalars are computed
-//    redundantly by every thread off the critical path: two CTA barriers per column instead of four.
-// A flag-in-data ("LL") exchange with per-warp remote stores was measured and rejected: the SM-to-SM network costs
-// ~3.5 cycles per 16-byte packet, 4600 cycles per round (tools/probe/probe_ll.cu, profiles/r02_probe_ll.json).
-// ------------------------------------------------------------------------------------------------------------------
-struct SytrdFusedSmem {
-  double rbuf[2][EIG_CL][SYTRD_MSG];  // received messages, one per source CTA: p[32], column slice[32], p.v, pad
-  double sbuf[2][SYTRD_MSG];          // my outgoing message
-  double xh[2][EIG_NMAX];             // masked current column (zero for rows <= j)
-  double vf[2][EIG_NMAX];             // Householder vector of column j
-  double wf[2][EIG_NMAX];             // w of column j
-  double nrm[2][16];                  // per-warp partial squared norms of the next column
-  double dpart[16];                   // per-warp partial p.v
-  unsigned long long bars[2];
-};
-
-__global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_NT, 1)
-k_sytrd_fused(const double* __restrict__ G, int ld, int n, double* __restrict__ d, double* __restrict__ e,
-              double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status, long long* __restrict__ prof) {
-  extern __shared__ __align__(16) unsigned char sytrd_raw[];
-  SytrdFusedSmem& S = *reinterpret_cast<SytrdFusedSmem*>(sytrd_raw);
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int me = (int)cluster_ctarank();
-  const int half = lane >> 4;
-  const int row0 = me + 2 * EIG_CL * warp, row1 = row0 + EIG_CL;   // global rows of this warp
-  const int myrow = half ? row1 : row0;                            // the row this lane reports after the reduction
-  const int mylr = 2 * warp + half;                                // its local index (0..31)
-  double a[2][8][2];
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int r = rr ? row1 : row0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = 64 * i + 2 * lane;
-      a[rr][i][0] = (r < n && c < n) ? G[(size_t)r * ld + c] : 0.0;          // G is symmetric
-      a[rr][i][1] = (r < n && c + 1 < n) ? G[(size_t)r * ld + c + 1] : 0.0;
-    }
-  }
-  double x = t < n ? G[t] : 0.0;                                    // full column 0 (one entry per thread)
-  S.xh[0][t] = t > 0 ? x : 0.0;
-  {
-    const double s = warp_sum(t > 1 ? x * x : 0.0);
-    if (lane == 0) S.nrm[0][warp] = s;
-  }
-  if (t == 0) {
-    mbar_init(eig_smem_u32(&S.bars[0]), 1);
-    mbar_init(eig_smem_u32(&S.bars[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  cluster_sync_all();                             // every CTA resident, barriers initialised
-  bool ok = true;
-  // optional phase clocks (prof != nullptr): lane 0 of warps 0 and 15 of CTA 0 accumulate the cycles between the marks
-  const bool pr = prof != nullptr && me == 0 && lane == 0 && (warp == 0 || warp == 15);
-  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0, sub[3] = {0, 0, 0};
-#define SY_MARK(i) do { if (pr) { const long long now_ = clock64(); ph[i] += now_ - tc; tc = now_; } } while (0)
-  if (pr) tc = clock64();
-  for (int j = 0; j + 2 < n; ++j) {
-    const int par = j & 1;
-    const double* __restrict__ xhp = S.xh[par];
-    const double* __restrict__ pv = S.vf[par ^ 1];
-    const double* __restrict__ pw = S.wf[par ^ 1];
-    const double alpha = xhp[j + 1];
-    // ---- one pass over the registers: rank-2 update of column j-1, then q = A xh on my two rows
-    double q0[4] = {0.0, 0.0, 0.0, 0.0}, q1[4] = {0.0, 0.0, 0.0, 0.0};
-    if (row1 > j) {                                // warp-uniform: both rows finished -> nothing to do
-      const bool live0 = row0 > j, upd = j > 0;
-      const double nv0 = -pv[row0], nw0 = -pw[row0], nv1 = -pv[row1], nw1 = -pw[row1];
-      const int ib0 = (j + 1) >> 6;               // column blocks below ib0 are finished for every lane
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i < ib0) continue;
-        const int c = 64 * i + 2 * lane;
-        const double2 xx = *reinterpret_cast<const double2*>(&xhp[c]);
-        if (upd) {
-          const double2 vv = *reinterpret_cast<const double2*>(&pv[c]);
-          const double2 ww = *reinterpret_cast<const double2*>(&pw[c]);
-          a[1][i][0] = fma(nv1, ww.x, fma(nw1, vv.x, a[1][i][0]));
-          a[1][i][1] = fma(nv1, ww.y, fma(nw1, vv.y, a[1][i][1]));
-          if (live0) {
-            a[0][i][0] = fma(nv0, ww.x, fma(nw0, vv.x, a[0][i][0]));
-            a[0][i][1] = fma(nv0, ww.y, fma(nw0, vv.y, a[0][i][1]));
-          }
-        }
-        q1[2 * (i & 1)] = fma(a[1][i][0], xx.x, q1[2 * (i & 1)]);
-        q1[2 * (i & 1) + 1] = fma(a[1][i][1], xx.y, q1[2 * (i & 1) + 1]);
-        if (live0) {
-          q0[2 * (i & 1)] = fma(a[0][i][0], xx.x, q0[2 * (i & 1)]);
-          q0[2 * (i & 1) + 1] = fma(a[0][i][1], xx.y, q0[2 * (i & 1) + 1]);
-        }
-      }
-    }
-    SY_MARK(0);                                    // fused pass
-    // ---- my rows' entries of column j+1 (after update j-1): held by lane ((j+1) & 63) >> 1
-    double sl0 = 0.0, sl1 = 0.0;
-    {
-      const int cj = j + 1, kb = cj & 1;
-      switch (cj >> 6) {                           // block-uniform
-        case 0: sl0 = kb ? a[0][0][1] : a[0][0][0]; sl1 = kb ? a[1][0][1] : a[1][0][0]; break;
-        case 1: sl0 = kb ? a[0][1][1] : a[0][1][0]; sl1 = kb ? a[1][1][1] : a[1][1][0]; break;
-        case 2: sl0 = kb ? a[0][2][1] : a[0][2][0]; sl1 = kb ? a[1][2][1] : a[1][2][0]; break;
-        case 3: sl0 = kb ? a[0][3][1] : a[0][3][0]; sl1 = kb ? a[1][3][1] : a[1][3][0]; break;
-        case 4: sl0 = kb ? a[0][4][1] : a[0][4][0]; sl1 = kb ? a[1][4][1] : a[1][4][0]; break;
-        case 5: sl0 = kb ? a[0][5][1] : a[0][5][0]; sl1 = kb ? a[1][5][1] : a[1][5][0]; break;
-        case 6: sl0 = kb ? a[0][6][1] : a[0][6][0]; sl1 = kb ? a[1][6][1] : a[1][6][0]; break;
-        default: sl0 = kb ? a[0][7][1] : a[0][7][0]; sl1 = kb ? a[1][7][1] : a[1][7][0]; break;
-      }
-      const int src = (cj & 63) >> 1;
-      sl0 = __shfl_sync(0xffffffffu, sl0, src);
-      sl1 = __shfl_sync(0xffffffffu, sl1, src);
-    }
-    const double slice = half ? sl1 : sl0;
-    // ---- Householder scalars (every thread, bit-identical everywhere) -- independent of the reduction below
-    double beta = alpha, tj = 0.0, scale = 0.0;
-    {
-      double nr[8];                                // partial norms of column j: fixed tree, identical in every thread
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const double2 v2 = *reinterpret_cast<const double2*>(&S.nrm[par][2 * k]);
-        nr[k] = v2.x + v2.y;
-      }
-#pragma unroll
-      for (int w = 4; w > 0; w >>= 1)
-#pragma unroll
-        for (int k = 0; k < w; ++k) nr[k] += nr[k + w];
-      const double xn2 = nr[0];
-      if (xn2 != 0.0) {
-        const double nn = fma(alpha, alpha, xn2);
-        const double rinv = fast_rsqrt(nn);                     // 1/|beta|
-        beta = -copysign(nn * rinv, alpha);
-        tj = (beta - alpha) * (-copysign(rinv, alpha));          // (beta - alpha) / beta
-        scale = fast_rcp(alpha - beta);
-      }
-    }
-    const double vt = (t > j + 1) ? x * scale : (t == j + 1 ? 1.0 : 0.0);
-    S.vf[par][t] = vt;
-    SY_MARK(1);                                    // slice broadcast + Householder scalars
-    // ---- row sums: the first round moves row 0 onto lanes 0-15 and row 1 onto lanes 16-31
-    double qs;
-    {
-      const double s0 = (q0[0] + q0[1]) + (q0[2] + q0[3]), s1 = (q1[0] + q1[1]) + (q1[2] + q1[3]);
-      const double send = half ? s0 : s1, keep = half ? s1 : s0;
-      qs = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
-    }
-    {
-      const double p = (myrow > j && myrow < n) ? (tj * scale) * fma(-beta, slice, qs) : 0.0;
-      const double vr = (myrow > j + 1) ? xhp[myrow] * scale : (myrow == j + 1 ? 1.0 : 0.0);
-      double dp = p * vr;
-      dp += __shfl_xor_sync(0xffffffffu, dp, 16);
-      if ((lane & 15) == 0) {
-        S.sbuf[par][mylr] = p;
-        S.sbuf[par][EIG_LR + mylr] = slice;
-        if (lane == 0) S.dpart[warp] = dp;
-        fence_proxy_async_smem();                  // my generic-proxy writes precede the bulk copies issued after the barrier
-      }
-    }
-    if (me == (j & (EIG_CL - 1))) {
-      V[(size_t)j * EIG_LDV + t] = vt;
-      if (t == 0) { e[j] = beta; tau[j] = tj; }
-    }
-    if (me == 0 && t == j) d[j] = x;
-    SY_MARK(2);                                    // row sums, p, partial dot, message
-    __syncthreads();                               // message complete
-    SY_MARK(3);                                    // barrier
-    if (warp == 0) {
-      double dsum = lane < 16 ? S.dpart[lane] : 0.0;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-      if (pr) { const long long now_ = clock64(); sub[0] += now_ - tc; }
-      if (lane == 0) {
-        S.sbuf[par][2 * EIG_LR] = dsum;
-        fence_proxy_async_smem();
-        if (pr) { const long long now_ = clock64(); sub[1] += now_ - tc; }
-        mbar_expect_tx(eig_smem_u32(&S.bars[par]), SYTRD_TX_BYTES);
-      }
-      __syncwarp();
-      if (pr) { const long long now_ = clock64(); sub[2] += now_ - tc; }
-      if (lane < EIG_CL)
-        bulk_copy_to_cta(mapa_u32(eig_smem_u32(&S.rbuf[par][me][0]), lane), eig_smem_u32(&S.sbuf[par][0]), SYTRD_MSG * 8,
-                         mapa_u32(eig_smem_u32(&S.bars[par]), lane));
-    }
-    SY_MARK(4);                                    // (warp 0) dot sum + bulk copies issued
-    ok = mbar_wait_cluster(eig_smem_u32(&S.bars[par]), (uint32_t)((j >> 1) & 1)) && ok;
-    SY_MARK(5);                                    // exchange wait
-    // ---- w, the next full column and its partial norms
-    double dsum[EIG_CL / 2];
-#pragma unroll
-    for (int c = 0; c < EIG_CL / 2; ++c) dsum[c] = S.rbuf[par][2 * c][2 * EIG_LR] + S.rbuf[par][2 * c + 1][2 * EIG_LR];
-#pragma unroll
-    for (int w = EIG_CL / 4; w > 0; w >>= 1)
-#pragma unroll
-      for (int c = 0; c < w; ++c) dsum[c] += dsum[c + w];       // fixed tree: identical in every thread of every CTA
-    const double al2 = -0.5 * tj * dsum[0];
-    const double wt = fma(al2, vt, S.rbuf[par][t & 15][t >> 4]);
-    const double wj1 = S.rbuf[par][(j + 1) & 15][(j + 1) >> 4] + al2;   // v[j+1] = 1
-    const double xnew = S.rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);      // column j+1 of A - v w^T - w v^T
-    S.wf[par][t] = wt;
-    S.xh[par ^ 1][t] = (t > j + 1) ? xnew : 0.0;
-    {
-      const double s = warp_sum(t > j + 2 ? xnew * xnew : 0.0);
-      if (lane == 0) S.nrm[par ^ 1][warp] = s;
-    }
-    x = xnew;
-    SY_MARK(6);                                    // w, next column, partial norms
-    __syncthreads();
-    SY_MARK(7);                                    // barrier
-  }
-  if (pr) for (int i = 0; i < 8; ++i) prof[(warp == 0 ? 0 : 8) + i] = ph[i];
-  if (pr && warp == 0) for (int i = 0; i < 3; ++i) prof[16 + i] = sub[i];
-#undef SY_MARK
-  // ---- trailing 2 x 2 block: x is column n-2 (n >= 2) or column 0; element (n-1, n-1) still lacks update n-3
-  if (me == 0) {
-    if (n >= 2) {
-      if (t == n - 2) d[n - 2] = x;
-      if (t == n - 1) e[n - 2] = x;
-    } else if (t == 0) d[0] = x;
-  }
-  if (n >= 2) {
-    const int last = n - 3;                                     // pending update (none if n == 2)
-    double corr = 0.0;
-    if (last >= 0) corr = -2.0 * S.vf[last & 1][n - 1] * S.wf[last & 1][n - 1];
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = rr ? row1 : row0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          if (r == n - 1 && 64 * i + 2 * lane + k == n - 1) d[n - 1] = a[rr][i][k] + corr;
-    }
   }
   if (!ok && t == 0) atomicExch(status, 3);
   cluster_sync_all();                             // nobody exits while a peer could still address its shared memory

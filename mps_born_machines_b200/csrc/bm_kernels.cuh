@@ -1387,6 +1387,12 @@ __global__ void k_finish_logpsi(const double* __restrict__ E, int ld, const int*
   sign[i] = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
 }
 
+// A[i][i] = 1 + i/n (distinct diagonal: warm-up input of the cuSOLVER fallback)
+__global__ void k_set_diag(double* __restrict__ A, int n, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[(size_t)i * ld + i] = 1.0 + (double)i / n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // batched general-mask reconstruction (TNutils.py:2053-2116 for B images sharing one mask)
 //   right pass: E_j[b] = sum over the admissible x of M_j[x] E_{j+1}[b] M_j[x]^T  (k_dgemm, per-image operand selection)

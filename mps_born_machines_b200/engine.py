@@ -456,6 +456,15 @@ class BornEngine:
         return lam, U, {'ms': info[0], 'ortho_dev': info[1], 'on_chip': bool(info[2]),
                         'stage_ms': dict(zip(('sytrd', 'eigvals', 'vectors', 'reflectors', 'polish'), info[3:8].tolist()))}
 
+    FALLBACK_REASONS = ('cluster_unavailable', 'nonfinite', 'zero_matrix', 'too_many_levels', 'unresolved_kept_values',
+                        'degenerate_kept_eigenvalues', 'orthonormality_check_failed', 'unused')
+
+    def eig_fallback_reasons(self):
+        """why splits left the on-chip eigensolver (counts since the engine was created)."""
+        out = (C.c_longlong * 8)()
+        check(self._ctx, self._lib.bm_eig_fallback_reasons(self._ctx, out))
+        return {k: int(v) for k, v in zip(self.FALLBACK_REASONS, out) if v}
+
     def eig_stats(self):
         """(splits that ran on the on-chip eigensolver, splits that fell back to cuSOLVER syevd)"""
         a, b, lv = C.c_longlong(), C.c_longlong(), C.c_int()

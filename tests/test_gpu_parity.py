@@ -733,3 +733,28 @@ def test_gradient_is_bitwise_reproducible_over_repeats(bm, precision):
             again = eng.step_grad(3).cpu().numpy()
             assert np.array_equal(first, again)
         eng.close()
+
+
+def test_split_with_nearly_degenerate_singular_values_stays_on_chip(bm):
+    """two kept singular values 1e-12 apart (relative): the twisted-factorisation vectors of the pair overlap by ~1e-3,
+    a second Newton-Schulz round restores orthonormality on the device (no cuSOLVER fallback); the isometry is exact to
+    1e-12 and the singular values match.  An exactly degenerate pair still takes the cuSOLVER levels."""
+    rng = np.random.default_rng(77)
+    D = 8
+    for rel_gap, expect_fallback in ((1e-12, 0), (0.0, 1)):
+        s = np.array([1.0, 0.9, 0.8 * (1 + rel_gap), 0.8, 0.5, 0.4, 0.3, 0.2])
+        U, _ = np.linalg.qr(rng.standard_normal((2 * D, D)))
+        V, _ = np.linalg.qr(rng.standard_normal((2 * D, D)))
+        m1 = (U * s).reshape(D, 2, D).transpose(0, 2, 1)               # rows (a,p) -> [a][b][p]
+        m2 = V.T.reshape(D, D, 2)                                       # [b][(c,q)] -> [b][c][q]
+        mps = [rng.standard_normal((D, 2)), m1, m2, rng.standard_normal((D, 2))]
+        eng = engine_for(bm, mps, cap=D)
+        out = eng.split_bond(1, going_right=True, max_bond=D, cutoff=1e-10, want_s=True)
+        np.testing.assert_allclose(out['s'], np.sort(s)[::-1], rtol=1e-9)
+        left = eng.get_site(1).transpose(0, 2, 1).reshape(2 * D, -1)
+        np.testing.assert_allclose(left.T @ left, np.eye(D), atol=1e-12)
+        A = np.einsum('abp,bcq->apcq', eng.get_site(1), eng.get_site(2)).reshape(2 * D, 2 * D)
+        np.testing.assert_allclose(A, (U * s) @ V.T, atol=1e-12)
+        fast, fallback = eng.eig_stats()
+        assert (fast, fallback) == (1 - expect_fallback, expect_fallback), (rel_gap, fast, fallback, eng.eig_fallback_reasons())
+        eng.close()
