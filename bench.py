@@ -23,10 +23,11 @@ import tempfile
 import threading
 import time
 
-# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm (numpy on the host cores) must use
-# all of them, so the BLAS/OpenMP pools are sized BEFORE numpy is imported (the N>1 reference lines ran
-# on one thread).  Our own arm does not compute on the host; its CPU baseline leg (N=1 only) wants the same.
-if '--impl' in sys.argv and 'reference' in sys.argv or os.environ.get('OMP_NUM_THREADS') == '1':
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm (numpy on the host cores, rank 0
+# only) must use all of them, so its BLAS/OpenMP pools are sized BEFORE numpy is imported (the N>1
+# reference lines ran on one thread).  Our own arm keeps the launcher's setting: N ranks with a full-size pool each
+# oversubscribe the host during set-up (the QR sweeps of the random MPS took minutes instead of seconds).
+if '--impl' in sys.argv and 'reference' in sys.argv and os.environ.get('RANK', '0') == '0':
     for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
         os.environ[_v] = str(os.cpu_count())
 
@@ -246,6 +247,11 @@ def workload_config(name, world):
 
 
 # ------------------------------------------------------------------------------------------------------
+def trace(msg):
+    if os.environ.get('BENCH_TRACE'):
+        print(f"[bench rank {os.environ.get('RANK', '0')} t={time.time() % 1000:.1f}] {msg}", file=sys.stderr, flush=True)
+
+
 def measure_steps(args, workload, rank, world, local, full=True):
     """Set up `workload` on this rank's shard and time `args.steps` mid-chain two-site steps (device-resident inputs,
     CUDA events per step).  full=True adds the e2e loops, the per-kernel roofline pass, the full-chain sweep and the
@@ -282,6 +288,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
             eng.enable_peer_allreduce()
         except Exception as exc:          # e.g. CUDA IPC unavailable in this container: fall back to NCCL, say so
             allreduce_mode = f'nccl (peer-memory path unavailable: {exc})'
+    trace('setup done')
     eng.env_build(start)
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
@@ -308,6 +315,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     for _ in range(warm):
         eng.step(k, 1e-3, True, **kw); k += 1
 
+    trace('warm-up done')
     # ---- timed: EXACTLY `steps` steps, device-resident inputs
     l0 = eng.launch_count()
     eig0 = eng.eig_stats()
@@ -346,6 +354,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
         eng.close()
         return rec
 
+    trace('timed region done')
     # ---- e2e (a): the reference's own call sequence through the facade with HOST tensors, every step:
     #      learning_step_cached -> write the two tensors back into the host MPS -> sequential_update
     #      (TNutils.py:1603-1620).  Uploads 4 site tensors and downloads 2 per step (pageable numpy memory, as a
@@ -369,6 +378,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     e2e = {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps, 'd2h_bytes_per_step': d2h // steps,
            'api': 'facade TNutils.learning_step_cached + write-back + sequential_update, host numpy tensors in and out'}
 
+    trace('facade e2e done')
     # ---- e2e (b): the engine-level call with PINNED host site tensors (BornEngine.learning_step_host)
     host = {}
     def pinned(a):
@@ -392,6 +402,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
                              'api': 'BornEngine.learning_step_host, pinned host site tensors'}
     rec['e2e'] = e2e
 
+    trace('engine e2e done')
     # ---- per-kernel pass for the roofline (separate, events around each hot launch)
     eng.set_timing(True)
     for _ in range(max(3, min(steps, 8))):
@@ -420,6 +431,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
                        'whole_step_tflops': 6.0 * D * D * n_loc / (dev_ms / steps * 1e-3) / 1e12,
                        'whole_step_frac': 6.0 * D * D * n_loc / (dev_ms / steps * 1e-3) / 1e12 / fp64_peak}
 
+    trace('roofline pass done')
     # ---- a FULL two-site sweep (there and back, 2(L-1) steps over the whole chain incl. the narrow bonds at the ends),
     #      timed on the device as one region: the north star's sweeps/s, measured instead of extrapolated
     if not args.no_sweep:
@@ -438,6 +450,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
                              'skipped_steps': int(sum(1 for o_ in outs if o_['skipped'])),
                              'max_chi': int(max(o_['chi'] for o_ in outs))}
 
+    trace('sweep done')
     # ---- secondary metric of BASELINE.json: samples generated / s (batched ancestral sampler, device-resident).
     #      Reuses this engine: the sampler's arithmetic and cost do not depend on the gauge (config 4 itself is below).
     if world == 1 and not args.no_sampler:
@@ -667,4 +680,7 @@ def main():
 
 
 if __name__ == '__main__':
+    if os.environ.get('BENCH_TRACE'):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get('BENCH_TRACE_DUMP_S', '90')), exit=True)
     main()

@@ -1,9 +1,9 @@
 """Worker of tests/test_gpu_multirank.py: one process per rank (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* in the
 environment), every rank drives its own BornEngine through libbm.so on its sample shard.
 
-With >= WORLD_SIZE GPUs each rank owns one GPU and the control plane is NCCL; on a single-GPU box all ranks share
-cuda:0 (time-sliced contexts) and the control plane is gloo -- the fused peer-memory all-reduce kernel
-(k_grad_reduce_peer, CUDA IPC buffers) is the same code either way.
+With >= WORLD_SIZE GPUs each rank owns one GPU and the control plane is NCCL (both all-reduce flavours run); on a
+single-GPU box all ranks share cuda:0 (time-sliced contexts), the control plane is gloo and only the
+torch.distributed all-reduce is exercised (the fused peer kernel spins on its peers' flags and needs them co-resident).
 
 modes:  teacher   before every step a standalone single-GPU engine is loaded with the sharded run's tensors; both take
                   the step: chi, singular values, sum ln|psi| and Z must agree; replicas stay bitwise identical.
