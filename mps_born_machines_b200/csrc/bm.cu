@@ -1025,7 +1025,7 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     P.Renv = c->slot(k + 2); P.ldR = c->ldcap; P.Dr = Dr;
     P.winv = c->winv; P.perm = perm; P.goff = goff; P.ngroups = G; P.d = d;
     P.kchunk = kchunk; P.ws = c->ws; P.ws_stride = (long long)rows * ldA; P.ldA = ldA; P.ldRpad = ldr; P.tiles_c = tiles_c;
-    dim3 grid(std::max(nsplit, 1), tiles_a * tiles_c, G);
+    dim3 grid(tiles_a * tiles_c, std::max(nsplit, 1), G);
     {
       Timer t_(c, 2);
       if (tf32) k_grad_tf32<<<grid, TF_THREADS, sizeof(GradTf32Smem), c->stream>>>(P, c->tf_status);
