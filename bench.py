@@ -667,7 +667,7 @@ def main():
     ap.add_argument('--no-others', action='store_true', help='skip the short runs of BASELINE configs 2, 4, 5')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
                     help='multi-GPU gradient exchange: fused reduce + peer-memory all-reduce kernel, or NCCL')
-    ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32'],
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32', 'tf32_reg'],
                     help="fp64 (default, 1e-6 parity) or tf32 (gradient accumulation on tcgen05/TMEM, 1e-3 parity)")
     ap.add_argument('--sampler-bond', type=int, default=500)
     args = ap.parse_args()

@@ -66,7 +66,9 @@ int bm_eig_stats(bm_ctx* ctx, long long* on_chip, long long* fallback, int* last
  * numerically degenerate (closer than 1e-14 of the largest), [6] orthonormality check failed after the polish, [7] unused */
 int bm_eig_fallback_reasons(bm_ctx* ctx, long long* out8);
 /* grad_tf32 = 1: accumulate S = sum psi'/psi with tcgen05.mma.kind::tf32 into TMEM (1e-3 parity class; bonds <= 256,
- * larger bonds fall back to the FP64 DMMA kernel).  psi, environments, update and split stay FP64. */
+ * larger bonds fall back to the FP64 DMMA kernel), operands converted and staged by the threads; grad_tf32 = 2: the same
+ * contraction with TMA-staged operands (grouped FP32 copies written by one packing pass, cp.async.bulk.tensor boxes with
+ * the 128-byte swizzle feeding MN-major tcgen05 descriptors).  psi, environments, update and split stay FP64. */
 int bm_set_precision(bm_ctx* ctx, int grad_tf32);
 
 /* a1: stater/tens_picture (TNutils.py:446-455), torchized_imgs (:1011-1027).  Uploads the training

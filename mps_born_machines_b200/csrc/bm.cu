@@ -50,7 +50,10 @@ struct bm_ctx {
   cusolverDnHandle_t cusolver = nullptr;
   gesvdjInfo_t gesvdj = nullptr;
   int svd_method = BM_SVD_GESVDJ;
-  int grad_tf32 = 0;            // 1: gradient accumulation on tcgen05 (TF32 operands, FP32 TMEM accumulators)
+  int grad_tf32 = 0;            // 1: gradient accumulation on tcgen05 (TF32 operands, FP32 TMEM accumulators), register-staged;
+                                // 2: the same with TMA-staged operands (k_pack_tf32 + k_grad_tf32_tma)
+  float* tfL = nullptr; float* tfR = nullptr; size_t tf_rows = 0;   // packed FP32 operands [rows][256] of the TMA path
+  CUtensorMap tmL, tmR;         // tensor maps over tfL / tfR: box 32 rows x 32 floats, 128-byte swizzle with 32-byte atoms
   int* tf_status = nullptr;     // device flag raised by a bounded mbarrier wait that timed out
   long long launches = 0;
   int n_sm = 148, panel_ctas = 296;
@@ -204,6 +207,7 @@ int set_func_attrs(bm_ctx* c) {
   CU(cudaFuncSetAttribute(k_sample_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
   CU(cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradSmem)));
   CU(cudaFuncSetAttribute(k_grad_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradTf32Smem)));
+  CU(cudaFuncSetAttribute(k_grad_tf32_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradTmaSmem) + 1024));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, c->device));
   c->n_sm = prop.multiProcessorCount;
@@ -415,6 +419,36 @@ int eig_wy_factors(bm_ctx* c, int n) {
   k_wy_T<<<(nrefl + WY_B - 1) / WY_B, 1024, wy_T_smem_bytes(n), c->stream>>>(c->eV, EIG_LDV, c->eTau, n, nrefl, c->eT);
   c->launches++;
   KCHECK();
+  return BM_OK;
+}
+
+// packed FP32 operand buffers + tensor maps of the TMA-staged TF32 gradient (grown on demand)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int ensure_tma_operands(bm_ctx* c, size_t rows) {
+  if (rows <= c->tf_rows) return BM_OK;
+  rows = (rows + 1023) & ~(size_t)1023;
+  DALLOC(c->tfL, rows * TM_LD); DALLOC(c->tfR, rows * TM_LD);
+  c->tf_rows = 0;
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)TM_LD, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)TM_LD * sizeof(float)};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  for (int i = 0; i < 2; ++i) {
+    CUresult r = encode(i ? &c->tmR : &c->tmL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, i ? (void*)c->tfR : (void*)c->tfL, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, BM_ECUDA, "cuTensorMapEncodeTiled failed with status " + std::to_string((int)r));
+  }
+  c->tf_rows = rows;
   return BM_OK;
 }
 
@@ -634,7 +668,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->tfL, c->tfR, c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -767,7 +801,7 @@ int bm_eig_fallback_reasons(bm_ctx* c, long long* out8) {
 
 int bm_set_precision(bm_ctx* c, int grad_tf32) {
   if (!c) return BM_EINVAL;
-  c->grad_tf32 = grad_tf32 ? 1 : 0;
+  c->grad_tf32 = grad_tf32 == 2 ? 2 : (grad_tf32 ? 1 : 0);
   return BM_OK;
 }
 
@@ -998,6 +1032,8 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
   // ---- gradient accumulation
   {
     const bool tf32 = c->grad_tf32 && Dl <= TF_TILE && Dr <= TF_TILE;
+    const bool tma = tf32 && c->grad_tf32 == 2 && G <= TM_MAXG;
+    const int kstep = tma ? 32 : KC;              // a TMA box holds 32 samples: splits must not cut one
     const int tiles_a = tf32 ? 1 : (Dl + GT - 1) / GT, tiles_c = tf32 ? 1 : (Dr + GT - 1) / GT;
     int maxg = 0;
     for (int g = 0; g < G; ++g) maxg = std::max(maxg, h_goff[g + 1] - h_goff[g]);
@@ -1005,7 +1041,7 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     int kchunk = KC, nsplit = 0;
     {
       double best = 1e300;
-      for (int kc = KC; kc <= GRAD_MAXCHUNK; kc += KC) {
+      for (int kc = kstep; kc <= GRAD_MAXCHUNK; kc += kstep) {
         long long items = 0; int ns = 0;
         for (int g = 0; g < G; ++g) {
           int sg = (h_goff[g + 1] - h_goff[g] + kc - 1) / kc;
@@ -1026,7 +1062,27 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
     P.winv = c->winv; P.perm = perm; P.goff = goff; P.ngroups = G; P.d = d;
     P.kchunk = kchunk; P.ws = c->ws; P.ws_stride = (long long)rows * ldA; P.ldA = ldA; P.ldRpad = ldr; P.tiles_c = tiles_c;
     dim3 grid(tiles_a * tiles_c, std::max(nsplit, 1), G);
-    {
+    if (tma) {
+      // grouped, zero-padded FP32 copies of the operands (R scaled by 1/psi), then the TMA-staged tcgen05 contraction
+      PackParams Q{};
+      TmaGradParams T{};
+      int tot = 0;
+      for (int g2 = 0; g2 <= G; ++g2) {
+        Q.pgoff[g2] = T.pgoff[g2] = tot;
+        if (g2 < G) tot += (h_goff[g2 + 1] - h_goff[g2] + 31) & ~31;
+      }
+      int r2 = ensure_tma_operands(c, (size_t)tot + 32);
+      if (r2 != BM_OK) return r2;
+      Q.Lenv = P.Lenv; Q.ldL = P.ldL; Q.Dl = Dl; Q.Renv = P.Renv; Q.ldR = P.ldR; Q.Dr = Dr; Q.winv = c->winv; Q.perm = perm; Q.goff = goff;
+      Q.ngroups = G; Q.L32 = c->tfL; Q.R32 = c->tfR;
+      T.Dl = Dl; T.Dr = Dr; T.d = d; T.ngroups = G; T.kchunk = kchunk; T.ws = c->ws; T.ws_stride = P.ws_stride; T.ldA = ldA; T.ldRpad = ldr;
+      Timer t_(c, 2);
+      if (tot > 0) {
+        k_pack_tf32<<<std::min((tot + 7) / 8, 148 * 16), 256, 0, c->stream>>>(Q);
+        k_grad_tf32_tma<<<dim3(1, std::max(nsplit, 1), G), TF_THREADS, sizeof(GradTmaSmem) + 1024, c->stream>>>(c->tmL, c->tmR, T, c->tf_status);
+        c->launches++;
+      }
+    } else {
       Timer t_(c, 2);
       if (tf32) k_grad_tf32<<<grid, TF_THREADS, sizeof(GradTf32Smem), c->stream>>>(P, c->tf_status);
       else k_grad<<<grid, GRAD_THREADS, sizeof(GradSmem), c->stream>>>(P);

@@ -11,6 +11,7 @@
 //   k_grad        : S[x,y] += L_g^T diag(1/psi) R_g  (split over samples) (:1535-1536, psi' never materialised)
 //   k_sample_step : per-site conditional + branch selection               (generate_samples, :1847-1872)
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -773,6 +774,208 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_grad_tf32(GradParams P, int* 
     const int a = mt * 128 + (warp & 3) * 32 + lane;
     if (mt < mtiles) {
       // 16 columns per tcgen05.ld: every thread then writes 128 contiguous bytes (full sectors) of its row
+      for (int c0 = 0; c0 < npad; c0 += 16) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 256 + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a < P.Dl) {
+          double* orow = out + (long long)a * P.ldA + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            if (c0 + j + 1 < P.Dr)
+              *reinterpret_cast<double2*>(orow + j) = make_double2((double)__uint_as_float(r[j]), (double)__uint_as_float(r[j + 1]));
+            else if (c0 + j < P.Dr) orow[j] = (double)__uint_as_float(r[j]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged TF32 gradient kernel (precision = 'tf32'):  the same contraction as k_grad_tf32 with the operands staged by
+// the tensor-memory accelerator instead of by threads.
+//   k_pack_tf32       one pass over the samples of the step, in grouped order: L32[pp] = (float) L_n,
+//                     R32[pp] = (float)(R_n / psi_n); every pixel-pair group is padded with zero rows to a multiple of
+//                     32 rows, rows are 256 floats (zero beyond the bond), so that every TMA box is in bounds and a
+//                     box never mixes two groups.
+//   k_grad_tf32_tma   CTA = (split, group).  Warp 0 (one elected lane) is the producer: per chunk of 32 samples it
+//                     arms an mbarrier with the byte count and issues cp.async.bulk.tensor.2d loads of [32 rows x 32
+//                     floats] boxes with the 128-byte swizzle in 32-byte chunks -- exactly the canonical MN-major
+//                     SWIZZLE_128B_BASE32B operand atoms of tcgen05 (4 rows x 128 B, atoms along M/N 4096 B apart = one box).  Warp 1 (one elected
+//                     lane) issues tcgen05.mma.kind::tf32 (M = 128, N = Dr, K = 8) into TMEM and releases the stage with
+//                     tcgen05.commit.  All 8 warps run the epilogue (tcgen05.ld -> FP64 partial block in the split
+//                     workspace shared with k_grad / k_grad_reduce).
+// ------------------------------------------------------------------------------------------------
+constexpr int TM_LD = 256;                        // floats per packed row
+constexpr int TM_BOX_BYTES = 32 * 128;            // one box: 32 rows x 128 B
+constexpr int TM_OP_BYTES = (TM_LD / 32) * TM_BOX_BYTES;   // 32 KB per operand per stage
+constexpr int TM_STAGES = 3;
+constexpr int TM_MAXG = 16;
+
+struct TmaGradParams {
+  int Dl, Dr, d, ngroups, kchunk;
+  int pgoff[TM_MAXG + 1];                         // padded group offsets (multiples of 32 rows)
+  double* ws; long long ws_stride; int ldA, ldRpad;
+};
+struct PackParams {
+  const double* Lenv; long long ldL; int Dl;
+  const double* Renv; long long ldR; int Dr;
+  const double* winv; const int* perm; const int* goff;
+  int ngroups; int pgoff[TM_MAXG + 1];
+  float* L32; float* R32;
+};
+
+// one warp per packed row
+__global__ void __launch_bounds__(256) k_pack_tf32(PackParams P) {
+  const int lane = threadIdx.x & 31;
+  const int total = P.pgoff[P.ngroups];
+  for (int pp = blockIdx.x * 8 + (threadIdx.x >> 5); pp < total; pp += gridDim.x * 8) {
+    int g = 0;
+    while (g + 1 < P.ngroups && pp >= P.pgoff[g + 1]) ++g;
+    const int i = pp - P.pgoff[g];
+    const int cnt = P.goff[g + 1] - P.goff[g];
+    float* lo = P.L32 + (long long)pp * TM_LD;
+    float* ro = P.R32 + (long long)pp * TM_LD;
+    if (i < cnt) {
+      const long long id = P.perm ? P.perm[P.goff[g] + i] : P.goff[g] + i;
+      const double w = P.winv[id];
+      const double* lp = P.Lenv + id * P.ldL;
+      const double* rp = P.Renv + id * P.ldR;
+#pragma unroll
+      for (int k = 0; k < TM_LD / 64; ++k) {          // two consecutive columns per lane: 16-byte loads, 8-byte stores
+        const int cidx = 64 * k + 2 * lane;
+        float2 lv = make_float2(0.f, 0.f), rv = make_float2(0.f, 0.f);
+        if (cidx + 1 < P.Dl) { const double2 v = *reinterpret_cast<const double2*>(lp + cidx); lv = make_float2((float)v.x, (float)v.y); }
+        else if (cidx < P.Dl) lv.x = (float)lp[cidx];
+        if (cidx + 1 < P.Dr) { const double2 v = *reinterpret_cast<const double2*>(rp + cidx); rv = make_float2((float)(v.x * w), (float)(v.y * w)); }
+        else if (cidx < P.Dr) rv.x = (float)(rp[cidx] * w);
+        *reinterpret_cast<float2*>(lo + cidx) = lv;
+        *reinterpret_cast<float2*>(ro + cidx) = rv;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < TM_LD / 64; ++k) {
+        *reinterpret_cast<float2*>(lo + 64 * k + 2 * lane) = make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(ro + 64 * k + 2 * lane) = make_float2(0.f, 0.f);
+      }
+    }
+  }
+}
+
+struct GradTmaSmem {
+  unsigned char L[TM_STAGES][TM_OP_BYTES];
+  unsigned char R[TM_STAGES][TM_OP_BYTES];
+};
+// shared-memory matrix descriptor for MN-major TF32 operands.  The only swizzled layout tcgen05 accepts for them is
+// SWIZZLE_128B_BASE32B (32-byte chunks swizzled inside a 128-byte row: byte-address bits [5,7) ^= bits [7,9)), which
+// is what a TMA box with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces.  Canonical layout in units of 16 bytes:
+//   ((8, m), (4, k)) : ((1, LBO), (8, SBO));  LBO = distance between 128-byte atoms along M/N (one box), SBO = distance
+//   between groups of 4 K-rows (512 B for consecutive rows)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version 1 (sm_100)
+  d |= (uint64_t)1 << 61;            // SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int M, int N) {   // D = F32, A = B = TF32, both MN-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// grid = (1, max splits, ngroups); requires Dl, Dr <= 256, kchunk a multiple of 32
+__global__ void __launch_bounds__(TF_THREADS, 1) k_grad_tf32_tma(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+                                                                 TmaGradParams P, int* status) {
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B boxes need a 1024-byte aligned destination: align by hand (the launch asks for 1024 spare bytes)
+  GradTmaSmem& sm = *reinterpret_cast<GradTmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bars[2 * TM_STAGES + 1];   // full[3], empty[3], done
+  __shared__ uint32_t tmem_base_s;
+  const int g = blockIdx.z;
+  const int row0 = P.pgoff[g] + blockIdx.y * P.kchunk;
+  if (row0 >= P.pgoff[g + 1]) return;
+  const int cnt = min(P.kchunk, P.pgoff[g + 1] - row0);      // multiple of 32
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mtiles = (P.Dl + 127) / 128;
+  const int npad = (P.Dr + 15) & ~15;
+  const int nboxL = mtiles * 4, nboxR = (npad + 31) / 32;
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&bars[0]);
+  if (tid == 0) {
+    for (int s = 0; s <= 2 * TM_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8 * s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tmL) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tmR) : "memory");
+  }
+  if (warp == 0) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(&tmem_base_s);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const int nblk = cnt / 32;
+  bool alive = true;
+  if (warp == 0 && lane == 0) {
+    // ---- producer: TMA loads of the [32 x 32] boxes of one chunk, completion counted in bytes on full[st]
+    const uint32_t bytes = (uint32_t)(nboxL + nboxR) * TM_BOX_BYTES;
+    for (int blk = 0; blk < nblk && alive; ++blk) {
+      const int st = blk % TM_STAGES;
+      if (blk >= TM_STAGES) alive = mbar_wait_bounded(bar0 + 8 * (TM_STAGES + st), ((blk / TM_STAGES) - 1) & 1, status);
+      if (!alive) break;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar0 + 8 * st), "r"(bytes) : "memory");
+      const int row = row0 + blk * 32;
+      const uint32_t aL = (uint32_t)__cvta_generic_to_shared(sm.L[st]), aR = (uint32_t)__cvta_generic_to_shared(sm.R[st]);
+      for (int b = 0; b < nboxL; ++b) tma_load_2d(aL + b * TM_BOX_BYTES, &tmL, 32 * b, row, bar0 + 8 * st);
+      for (int b = 0; b < nboxR; ++b) tma_load_2d(aR + b * TM_BOX_BYTES, &tmR, 32 * b, row, bar0 + 8 * st);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer
+    const uint32_t idesc = umma_idesc_tf32_mn(128, npad);
+    for (int blk = 0; blk < nblk && alive; ++blk) {
+      const int st = blk % TM_STAGES;
+      alive = mbar_wait_bounded(bar0 + 8 * st, (blk / TM_STAGES) & 1, status);
+      if (!alive) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aL = (uint32_t)__cvta_generic_to_shared(sm.L[st]), aR = (uint32_t)__cvta_generic_to_shared(sm.R[st]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {                         // 8 samples per MMA
+        const uint64_t db = umma_desc_sw128(aR + ks * 1024, TM_BOX_BYTES, 512);
+        for (int mt = 0; mt < mtiles; ++mt) {
+          const uint64_t da = umma_desc_sw128(aL + mt * 4 * TM_BOX_BYTES + ks * 1024, TM_BOX_BYTES, 512);
+          const uint32_t acc = (blk > 0 || ks > 0) ? 1u : 0u;
+          asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                       :: "r"(tmem + (uint32_t)(mt * 256)), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar0 + 8 * (TM_STAGES + st)) : "memory");
+      if (blk == nblk - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar0 + 8 * 2 * TM_STAGES) : "memory");
+    }
+  }
+  __syncwarp();
+  // ---- epilogue: all MMAs done -> TMEM -> FP64 partial block in the split workspace
+  alive = mbar_wait_bounded(bar0 + 8 * 2 * TM_STAGES, 0, status);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (alive) {
+    const int p = g / P.d, q = g % P.d;
+    double* out = P.ws + (long long)blockIdx.y * P.ws_stride + (long long)p * P.Dl * P.ldA + (long long)q * P.ldRpad;
+    const int mt = warp >> 2;                       // warps 0-3: rows 0..127, warps 4-7: rows 128..255
+    const int a = mt * 128 + (warp & 3) * 32 + lane;
+    if (mt < mtiles) {
       for (int c0 = 0; c0 < npad; c0 += 16) {
         uint32_t r[16];
         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 256 + c0);

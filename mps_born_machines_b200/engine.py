@@ -42,9 +42,9 @@ class BornEngine:
         code = self._lib.bm_create(C.byref(self._ctx), self.device, self.L, self.d, self.Dcap, C.c_void_p(stream))
         check(self._ctx, code)
         check(self._ctx, self._lib.bm_set_svd(self._ctx, SVD[svd]))
-        if precision not in ('fp64', 'tf32'):
-            raise ValueError("precision must be 'fp64' or 'tf32'")
-        check(self._ctx, self._lib.bm_set_precision(self._ctx, 1 if precision == 'tf32' else 0))
+        if precision not in ('fp64', 'tf32', 'tf32_reg'):
+            raise ValueError("precision must be 'fp64', 'tf32' (TMA-staged tcgen05 gradient) or 'tf32_reg' (register-staged)")
+        check(self._ctx, self._lib.bm_set_precision(self._ctx, {'fp64': 0, 'tf32_reg': 1, 'tf32': 2}[precision]))
         self.precision = precision
         ld = (self.Dcap + 1) & ~1
         self._S = torch.zeros(self.d * self.Dcap * self.d * ld + 2, dtype=torch.float64, device=f'cuda:{self.device}')

@@ -342,12 +342,13 @@ def test_config2_mid_chain_steps(bm):
 # ------------------------------------------------------------------------------------------------------------------
 # TF32 family (tcgen05 + TMEM gradient accumulation): 1e-3 parity class
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('L,D,N,seed', [(10, 8, 300, 101), (8, 24, 1000, 102), (6, 5, 77, 103)])
-def test_tf32_gradient_matches_oracle(bm, L, D, N, seed):
+@pytest.mark.parametrize('precision', ['tf32', 'tf32_reg'])      # TMA-staged / register-staged operands
+@pytest.mark.parametrize('L,D,N,seed', [(10, 8, 300, 101), (8, 24, 1000, 102), (6, 5, 77, 103), (6, 200, 1500, 104)])
+def test_tf32_gradient_matches_oracle(bm, L, D, N, seed, precision):
     mps, imgs = make_problem(L, D, N, seed)
     phys = o.embed(imgs)
     d = 2
-    eng = bm.BornEngine(L, max(o.bond_sizes(mps)) * d, precision='tf32')
+    eng = bm.BornEngine(L, max(o.bond_sizes(mps)) * d, precision=precision)
     eng.set_mps(mps); eng.set_data(imgs)
     cache = o.EnvCache(mps, phys, 'pow2')
     for k in (0, 1, L // 2, L - 2):
@@ -682,9 +683,27 @@ def test_config5_shape_mid_chain_steps(bm):
     assert fast == 2 and fallback == 0
 
 
-def test_tf32_gradient_at_config3_shape(bm):
-    """precision='tf32' at D=256: singular values, sum ln|psi| and Z of one step within 1e-3 of the FP64 oracle."""
-    _teacher_forced(bm, 22, 256, 8192, 2, 9, [9, 10], True, seed=303, precision='tf32', tol=1e-3)
+@pytest.mark.parametrize('precision', ['tf32', 'tf32_reg'])
+def test_tf32_gradient_at_config3_shape(bm, precision):
+    """precision='tf32' (TMA-staged tcgen05) / 'tf32_reg' at D=256: singular values, sum ln|psi| and Z of one step
+    within 1e-3 of the FP64 oracle."""
+    _teacher_forced(bm, 22, 256, 8192, 2, 9, [9, 10], True, seed=303, precision=precision, tol=1e-3)
+
+
+def test_tf32_tma_and_register_staging_agree(bm):
+    """both TF32 gradient kernels round the same FP32 operands to TF32 and accumulate in FP32 TMEM: their results agree
+    to FP32 accumulation-order noise, far below the 1e-3 class (a wrong swizzle/descriptor would show up as O(1))."""
+    L, D, N = 8, 96, 5000
+    mps, imgs = make_problem(L, D, N, 611, centre=3)
+    out = {}
+    for precision in ('tf32', 'tf32_reg', 'fp64'):
+        eng = bm.BornEngine(L, D, precision=precision)
+        eng.set_mps(mps); eng.set_data(imgs)
+        out[precision] = eng.grad_to_ref(3, eng.step_grad(3))
+        eng.close()
+    scale = np.abs(out['fp64']).max()
+    assert np.abs(out['tf32'] - out['tf32_reg']).max() < 2e-5 * scale
+    assert np.abs(out['tf32'] - out['fp64']).max() < 3e-3 * scale
 
 
 def test_sampler_bond_500_bit_exact(bm):
@@ -721,7 +740,7 @@ def test_on_chip_eigensolver_size_sweep_is_exact_and_bitwise_reproducible(bm):
     eng.close()
 
 
-@pytest.mark.parametrize('precision', ['fp64', 'tf32'])
+@pytest.mark.parametrize('precision', ['fp64', 'tf32', 'tf32_reg'])
 def test_gradient_is_bitwise_reproducible_over_repeats(bm, precision):
     """20 repetitions of the same step_grad on several bond shapes (ragged groups, D not a multiple of the tiles)."""
     for L, D, N, seed in ((8, 32, 777, 1), (8, 48, 1500, 2), (8, 64, 4099, 3)):
