@@ -34,6 +34,8 @@ struct Chain {            // ping-pong state for left chains (logpsi, sampler)
   int* perm = nullptr;       // [n]
   int* goff = nullptr;       // [d+1]
   int* goff_all = nullptr;   // {0, n}
+  int* rej_list = nullptr;   // [n] rows whose first branch was rejected at the current site (two-phase sampler step)
+  int* rej_count = nullptr;  // {0, count}
   double* U = nullptr;       // uniforms
   size_t Ucap = 0;
   double* lnabs = nullptr; double* sign = nullptr;
@@ -97,6 +99,7 @@ struct bm_ctx {
   int two_round[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // level used a second Newton-Schulz round (close eigenvalues)
   int trivec3 = 1;              // 1: k_tri_vectors3 (three-term pivots), 0: k_tri_vectors (qd form; BM_TRIVEC=qd)
   int wy_back = 1;              // 1: blocked compact-WY back-transformation (k_wy_T + k_wy_apply), 0: k_apply_reflectors (BM_BACKTRANSFORM=warp)
+  int sample_fused = 0;         // BM_SAMPLE_FUSED=1: always the single-launch sampler step (both branches per 64-row tile)
   int wy_pending = 0;           // k_wy_T of the current reflectors is in flight on the side stream
   int eig_debug = 0;         // BM_EIG_DEBUG=1: per-level stage times of the on-chip split on stderr
   std::vector<std::pair<const char*, cudaEvent_t>> dbg_ticks;
@@ -289,6 +292,7 @@ int eig_setup(bm_ctx* c) {
   CU(cudaMallocHost((void**)&c->h_dev, DEV_SLOTS * sizeof(double)));
   c->eig_ok = 1;
   if (const char* dbg = std::getenv("BM_EIG_DEBUG")) c->eig_debug = std::atoi(dbg);
+  if (const char* v = std::getenv("BM_SAMPLE_FUSED")) c->sample_fused = std::atoi(v);
   if (c->eig_debug) for (auto& ev : c->eig_ev) CU(cudaEventCreate(&ev));
   return BM_OK;
 }
@@ -523,6 +527,7 @@ int chain_alloc(bm_ctx* c, int n) {
   DALLOC(ch.perm, n);
   DALLOC(ch.goff, c->d + 1);
   DALLOC(ch.goff_all, 2);
+  DALLOC(ch.rej_list, n); DALLOC(ch.rej_count, 2);
   { int h[2] = {0, n}; CU(cudaMemcpy(ch.goff_all, h, sizeof(h), cudaMemcpyHostToDevice)); }
   DALLOC(ch.lnabs, n);
   DALLOC(ch.sign, n);
@@ -671,7 +676,7 @@ int bm_destroy(bm_ctx* c) {
                   c->tfL, c->tfR, c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
-                  c->chain.goff, c->chain.goff_all, c->chain.U, c->chain.lnabs, c->chain.sign};
+                  c->chain.goff, c->chain.goff_all, c->chain.rej_list, c->chain.rej_count, c->chain.U, c->chain.lnabs, c->chain.sign};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->h_iscal) cudaFreeHost(c->h_iscal);
@@ -1611,8 +1616,21 @@ static int sample_loop(bm_ctx* c, int n, int rule, int start_site, const double*
     P.n = n; P.strict = rule == BM_RULE_SINGLE; P.pix_first = rule == BM_RULE_BATCHED ? 1 : 0;
     P.both_norm = (s == start_site);
     P.goff = ch.goff_all;
-    {
+    // large batches: two launches per site (first branch for all rows, second branch for the rejected rows only);
+    // small batches are launch-bound and the first site needs both norms: one fused launch
+    const bool two_phase = !P.both_norm && n >= 4096 && !c->sample_fused;
+    if (two_phase) {
+      CU(cudaMemsetAsync(ch.rej_count, 0, 2 * sizeof(int), c->stream));      // {0, count}: goff of phase 2
+      P.rej_list = ch.rej_list; P.rej_count = ch.rej_count + 1;
       Timer t_(c, 7);
+      P.phase = 1;
+      k_sample_step<<<grid, NTHREADS, PANEL_SMEM, c->stream>>>(P);
+      P.phase = 2; P.goff = ch.rej_count;
+      k_sample_step<<<grid, NTHREADS, PANEL_SMEM, c->stream>>>(P);
+      c->launches++;
+    } else {
+      Timer t_(c, 7);
+      P.phase = 0;
       k_sample_step<<<grid, NTHREADS, PANEL_SMEM, c->stream>>>(P);
     }
     c->launches++;

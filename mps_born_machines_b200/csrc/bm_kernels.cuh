@@ -1128,7 +1128,13 @@ struct SampleParams {
   const double* U;
   uint8_t* pix_out;
   int n; int strict; int pix_first; int both_norm;
-  const int* goff;     // {0, n}
+  const int* goff;     // {0, n}   (phase 2: {0, number of rejected rows}, written by phase 1)
+  // Two-phase step (the decision of a row needs only its FIRST branch unless both_norm): phase 1 computes the first
+  // branch of every row, decides, finishes the accepted rows and appends the rejected ones to `rej_list`; phase 2
+  // computes the second branch of the listed rows only -- the reference's flop count (2 D^2 (1 + share of rejections)
+  // per row) instead of both branches for every 64-row tile that holds one rejection.  phase 0: fused single launch.
+  int phase;
+  int* rej_list; int* rej_count;   // rej_count[0] doubles as goff[1] of phase 2 (rej_count[-1] == 0)
 };
 
 struct SampleShared {     // one copy for all tile heights (keeps the kernel at 2 CTAs / SM)
@@ -1153,7 +1159,7 @@ __device__ __forceinline__ void tile_sample(const SampleParams& P, unsigned char
   __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
   if (tid < TM) {
-    int id = tid < nrows ? row0 + tid : -1;
+    int id = tid < nrows ? (P.phase == 2 ? P.rej_list[row0 + tid] : row0 + tid) : -1;
     rowid[tid] = id;
     rowptr[tid] = id >= 0 ? P.Vin + (long long)id * P.ldv : nullptr;
     rscale[tid] = id >= 0 ? pow2d(-P.e_in[id]) : 0.0;
@@ -1215,6 +1221,16 @@ __device__ __forceinline__ void tile_sample(const SampleParams& P, unsigned char
     __syncthreads();
   };
 
+  if (P.phase == 2) {                            // second branch of the rejected rows (listed by phase 1)
+    pass(P.Bsecond, 0, n2s, m2s);
+    if (tid < TM && rowid[tid] >= 0) {
+      const int id = rowid[tid];
+      P.norm_out[id] = n2s[tid];
+      P.e_out[id] = frexp_exp(m2s[tid]);
+      P.pix_out[id] = (uint8_t)(1 - P.pix_first);
+    }
+    return;
+  }
   pass(P.Bfirst, 0, n1s, m1s);
   if (P.both_norm) pass(P.Bsecond, 1, n2s, m2s);
   int rej = 0;
@@ -1227,6 +1243,29 @@ __device__ __forceinline__ void tile_sample(const SampleParams& P, unsigned char
     int a = P.strict ? (u < p) : (u <= p);
     accs[tid] = a;
     rej = !a;
+  }
+  if (P.phase == 1) {                            // accepted rows are complete; rejected rows go to the list (one atomic per tile)
+    __shared__ int rej_base;
+    __syncthreads();
+    if (tid == 0) {
+      int cnt = 0;
+      for (int i = 0; i < TM; ++i) cnt += (rowid[i] >= 0 && !accs[i]);
+      rej_base = cnt ? atomicAdd(P.rej_count, cnt) : 0;
+    }
+    __syncthreads();
+    if (tid < TM && rowid[tid] >= 0) {
+      const int id = rowid[tid];
+      if (accs[tid]) {
+        P.norm_out[id] = n1s[tid];
+        P.e_out[id] = frexp_exp(m1s[tid]);
+        P.pix_out[id] = (uint8_t)P.pix_first;
+      } else {
+        int pos = rej_base;
+        for (int i = 0; i < tid; ++i) pos += (rowid[i] >= 0 && !accs[i]);
+        P.rej_list[pos] = id;
+      }
+    }
+    return;
   }
   if (__syncthreads_or(rej)) pass(P.Bsecond, 2, n2s, m2s);
   if (tid < TM && rowid[tid] >= 0) {
