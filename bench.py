@@ -316,7 +316,9 @@ def measure_steps(args, workload, rank, world, local, full=True):
         eng.step(k, 1e-3, True, **kw); k += 1
 
     trace('warm-up done')
-    # ---- timed: EXACTLY `steps` steps, device-resident inputs
+    # ---- timed: EXACTLY `steps` steps, device-resident inputs.  With per-step inputs larger than L2 (N = 1) the K steps
+    #      are ONE library call (BornEngine.sweep -> bm_sweep, what epoch() uses); otherwise L2 is flushed between the
+    #      steps and each step is its own call.
     l0 = eng.launch_count()
     eig0 = eng.eig_stats()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -324,19 +326,26 @@ def measure_steps(args, workload, rank, world, local, full=True):
     barrier()
     clocks.mark()
     wall0 = time.perf_counter()
-    for i in range(steps):
-        if flush is not None:
+    if flush is None:
+        ev[0][0].record()
+        outs = eng.sweep(list(range(k, k + steps)), 1, 1e-3, **kw); k += steps
+        ev[0][1].record()
+        chis = [o_['chi'] for o_ in outs]
+        eng.eig_stats(); levels = [eng.last_gram_levels]
+        ev = ev[:1]
+    else:
+        for i in range(steps):
             flush.fill_(i & 0xff)
             barrier()
-        ev[i][0].record()
-        out = eng.step(k, 1e-3, True, **kw); k += 1
-        ev[i][1].record()
-        chis.append(out['chi'])
-        eng.eig_stats(); levels.append(eng.last_gram_levels)
+            ev[i][0].record()
+            out = eng.step(k, 1e-3, True, **kw); k += 1
+            ev[i][1].record()
+            chis.append(out['chi'])
+            eng.eig_stats(); levels.append(eng.last_gram_levels)
     barrier()
     wall = time.perf_counter() - wall0
     clocks.mark()
-    step_ms = [round(a.elapsed_time(b), 3) for a, b in ev]
+    step_ms = [round(a.elapsed_time(b), 3) for a, b in ev]      # one entry per library call (the whole run when sweep() was used)
     launches = eng.launch_count() - l0
     eig1 = eng.eig_stats()
     dev_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
@@ -344,7 +353,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     value = N * steps / (dev_ms * 1e-3)
     rec = {'value': value, 'ms_per_step': dev_ms / steps, 'step_ms': step_ms, 'gram_levels': levels, 'chi': int(chis[-1]),
            'gpu_launches': int(launches), 'split_eig': {'on_chip': eig1[0] - eig0[0], 'cusolver_fallback': eig1[1] - eig0[1], 'fallback_reasons_since_setup': eng.eig_fallback_reasons()},
-           'wall_s_timed': wall, 'setup_s': t_setup, 'allreduce': allreduce_mode, 'clocks': clk, 'N': N, 'L': L, 'D': D, 'd': d}
+           'wall_s_timed': wall, 'setup_s': t_setup, 'allreduce': allreduce_mode, 'timed_call': 'sweep (one bm_sweep call)' if flush is None else 'step (L2 flushed between steps)', 'clocks': clk, 'N': N, 'L': L, 'D': D, 'd': d}
     if not full:
         eng.set_timing(True)
         for _ in range(3):

@@ -126,6 +126,14 @@ int bm_step(bm_ctx* ctx, int k, const int32_t* mask_host, int n_mask, double* S_
             double lr, int renorm, int going_right, int max_bond, double cutoff, double mom_bias, int advance,
             double* scalars_host, double* s_host);
 
+/* A run of two-site steps in one call: the loop body of learning_epoch_cached (TNutils.py:1597-1620) for the schedule
+ * bonds[i] / going_right[i], i < n_steps, each step as bm_step with advance = 1.  masks_host: n_steps x n_mask sample ids
+ * (NULL: full batch); mom_bias: one value per step (NULL: 0); scalars_host: n_steps x 8 (layout of bm_step_update).
+ * *n_done (may be NULL) = steps completed when the call returns (all of them unless an error code is returned). */
+int bm_sweep(bm_ctx* ctx, const int32_t* bonds, const int32_t* going_right, int n_steps, const int32_t* masks_host, int n_mask,
+             double* S_dev, double batch_total, double lr, int renorm, int max_bond, double cutoff, const double* mom_bias,
+             double* scalars_host, int* n_done);
+
 /* Merge + split of bond k without a gradient step or renormalisation: the primitive of `compress`,
  * `compress_copy`, `compress2` (TNutils.py:930-993) and of SVD-based canonicalisation sweeps. */
 int bm_split_bond(bm_ctx* ctx, int k, int going_right, int max_bond, double cutoff, double* scalars_host, double* s_host);

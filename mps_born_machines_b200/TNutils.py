@@ -570,10 +570,29 @@ def learning_epoch_cached(mps, *args, batch_size=25, update_wrap=None, lr_update
     L = len(mps.tensors)
     cost = []
     lr = _copy.copy(initial_lr)
+    sched = sweep_schedule(L)
     for epoch in range(epochs):
         print(f'epoch {epoch + 1}/{epochs}')
         going_right = True
-        for index in sweep_schedule(L):
+        # no momentum feedback between the two visits of a bond, no host callback, bounded bonds: the whole epoch is one
+        # library call (BornEngine.sweep); the masks are drawn first, in the order the step-by-step loop draws them
+        if not generic and max_bond and (owner is None or owner.t == 0):
+            masks = None
+            if batch_size < n:
+                masks = []
+                for _ in sched:
+                    np.random.shuffle(guide)
+                    masks.append(guide[:batch_size].copy())
+                masks = np.stack(masks)
+            outs = eng.sweep(sched, [1] * (L - 1) + [0] * (L - 1), _lr_value(lr), renorm, max_bond, cutoff, masks)
+            if owner is not None:
+                for index, out in zip(sched, outs):
+                    if not out['skipped']:
+                        owner.past_grad[index] = out['mean_dnll']
+            sched_loop = ()
+        else:
+            sched_loop = sched
+        for index in sched_loop:
             mask = None
             if batch_size < n:
                 np.random.shuffle(guide)

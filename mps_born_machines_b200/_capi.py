@@ -36,6 +36,7 @@ _SIGS = [
                                  C.c_double, _P, _P]),
     ('bm_step', C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
                           C.c_double, C.c_int, _P, _P]),
+    ('bm_sweep', C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, _P, _P, _P]),
     ('bm_split_bond', C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]),
     ('bm_get_merged', C.c_int, [_P, _P]),
     ('bm_ref_to_engine', C.c_int, [_P, C.c_int, _P, _P]),

@@ -1497,6 +1497,26 @@ int bm_step(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double* S_de
                      scalars_host, s_host);
 }
 
+// A run of two-site steps in ONE call: the loop of learning_epoch_cached (TNutils.py:1597-1620) without returning to
+// the caller between steps (no interpreter, no argument marshalling between the last kernel of a step and the first
+// of the next).  bonds[i] / going_right[i]: the schedule; masks_host: n_steps x n_mask sample ids (or null: full batch);
+// mom_bias: per-step momentum bias (or null); scalars_host: n_steps x 8 (as bm_step).  Stops at the first error and
+// reports how many steps completed in *n_done (may be null).
+int bm_sweep(bm_ctx* c, const int32_t* bonds, const int32_t* going_right, int n_steps, const int32_t* masks_host, int n_mask,
+             double* S_dev, double batch_total, double lr, int renorm, int max_bond, double cutoff, const double* mom_bias,
+             double* scalars_host, int* n_done) {
+  if (!c) return BM_EINVAL;
+  REQUIRE(bonds && going_right && n_steps >= 0 && scalars_host, "bm_sweep: bad arguments");
+  if (n_done) *n_done = 0;
+  for (int i = 0; i < n_steps; ++i) {
+    int r = bm_step(c, bonds[i], masks_host ? masks_host + (size_t)i * n_mask : nullptr, masks_host ? n_mask : 0, S_dev, batch_total, lr,
+                    renorm, going_right[i], max_bond, cutoff, mom_bias ? mom_bias[i] : 0.0, 1, scalars_host + (size_t)8 * i, nullptr);
+    if (r != BM_OK) return r;
+    if (n_done) *n_done = i + 1;
+  }
+  return BM_OK;
+}
+
 // merge + split only (no gradient step, no renormalisation): compress / canonicalisation sweeps
 // (TNutils.py:930-993 `compress*`: A.split(..., absorb='left', max_bond=...)).
 int bm_split_bond(bm_ctx* c, int k, int going_right, int max_bond, double cutoff, double* scalars_host, double* s_host) {

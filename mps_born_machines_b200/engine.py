@@ -322,9 +322,54 @@ class BornEngine:
         check(self._ctx, self._lib.bm_engine_to_ref(self._ctx, k, C.c_void_p(S.data_ptr()), _ptr(out)))
         return out
 
+    def sweep(self, bonds, going_right, lr, renorm='max', max_bond=None, cutoff=1e-10, masks=None, mom_bias=None,
+              batch_total=None):
+        """A run of two-site steps in ONE library call (bm_sweep): bonds[i] with direction going_right[i] (a bool or a
+        sequence), full batch or one mask per step (masks: (n_steps, n_mask) local sample ids).  Single GPU or the fused
+        peer all-reduce only (the torch.distributed all-reduce sits between the gradient and the update of every step).
+        Returns the list of per-step result dicts of `step` (without singular values)."""
+        if self.world > 1 and not self.peer:
+            raise RuntimeError('sweep() needs the fused peer all-reduce with several ranks; use step()/epoch()')
+        b = np.ascontiguousarray(np.asarray(bonds, dtype=np.int32))
+        n = b.size
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(going_right, dtype=np.int32), (n,)))
+        m = None
+        if masks is not None:
+            m = np.ascontiguousarray(np.asarray(masks, dtype=np.int32).reshape(n, -1))
+            if self.world > 1 and batch_total is None:
+                raise ValueError('multi-rank minibatch sweeps need batch_total')
+        if batch_total is None:
+            batch_total = self.N_total if m is None else m.shape[1]
+        mom = None if mom_bias is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mom_bias, dtype=np.float64), (n,)))
+        scal = np.zeros((n, 8))
+        done = C.c_int(0)
+        code = self._lib.bm_sweep(self._ctx, _ptr(b), _ptr(g), n, _ptr(m) if m is not None else None, m.shape[1] if m is not None else 0,
+                                  C.c_void_p(self._S.data_ptr()), float(batch_total), float(lr), RENORM[renorm],
+                                  int(max_bond) if max_bond else 0, float(cutoff), _ptr(mom) if mom is not None else None,
+                                  _ptr(scal), C.byref(done))
+        check(self._ctx, code)
+        outs = []
+        for i in range(n):
+            o = self._step_result(scal[i], None, False)
+            o['nll_batch'] = -2.0 * o['sum_logpsi'] / batch_total + math.log(o['Z']) if o['Z'] > 0 else float('nan')
+            outs.append(o)
+        return outs
+
     def epoch(self, lr, renorm='max', max_bond=None, cutoff=1e-10, batch_size=None, rng=None, callback=None):
-        """One reference epoch: 2(L-1) steps over the schedule, centre ends at site 0 (TNutils.py:1592-1625)."""
+        """One reference epoch: 2(L-1) steps over the schedule, centre ends at site 0 (TNutils.py:1592-1625).  Without a
+        per-step callback the whole epoch is ONE library call (bm_sweep)."""
         L = self.L
+        if callback is None and (self.world == 1 or self.peer):
+            sched = sweep_schedule(L)
+            dirs = [1] * (L - 1) + [0] * (L - 1)
+            use_mask = batch_size is not None and any(batch_size < n for n in self.shard_sizes)
+            masks, batch_total = None, None
+            if use_mask:
+                batch_total = sum(min(batch_size, n) for n in self.shard_sizes)
+                if batch_size < self.N:
+                    gen = rng if rng is not None else np.random
+                    masks = np.stack([gen.permutation(self.N)[:batch_size] for _ in sched])
+            return self.sweep(sched, dirs, lr, renorm, max_bond, cutoff, masks, None, batch_total)
         going_right = True
         outs = []
         # minibatches: `batch_size` samples PER RANK (all of a shard that is smaller).  Whether masks are used and the

@@ -777,3 +777,26 @@ def test_split_with_nearly_degenerate_singular_values_stays_on_chip(bm):
         fast, fallback = eng.eig_stats()
         assert (fast, fallback) == (1 - expect_fallback, expect_fallback), (rel_gap, fast, fallback, eng.eig_fallback_reasons())
         eng.close()
+
+
+def test_sweep_call_equals_step_by_step(bm):
+    """bm_sweep (one library call for a run of steps, TNutils.py:1597-1620) == the same steps one call at a time:
+    bitwise identical scalars and tensors, full batch and minibatch masks, both directions."""
+    L, D, N = 12, 8, 300
+    mps, imgs = make_problem(L, 4, N, 801)
+    rng = np.random.default_rng(802)
+    bonds = o.sweep_schedule(L)
+    dirs = [1] * (L - 1) + [0] * (L - 1)
+    for masks in (None, np.stack([rng.permutation(N)[:64] for _ in bonds])):
+        a = engine_for(bm, mps, imgs, cap=D); b = engine_for(bm, mps, imgs, cap=D)
+        outs = a.sweep(bonds, dirs, 0.05, 'l2', max_bond=D, masks=masks)
+        for i, k in enumerate(bonds):
+            ref = b.step(k, 0.05, bool(dirs[i]), 'l2', max_bond=D, mask=None if masks is None else masks[i])
+            for key in ('Z', 'sum_logpsi', 'chi', 'mean_dnll', 'renorm_div', 'trunc_err', 'nll_batch'):
+                assert outs[i][key] == ref[key], (i, key)
+        for x, y in zip(a.get_mps(), b.get_mps()):
+            assert np.array_equal(x, y)
+        # epoch() takes the same path
+        ea = a.epoch(0.05, 'l2', max_bond=D); eb = [b.step(k, 0.05, bool(dirs[i]), 'l2', max_bond=D) for i, k in enumerate(bonds)]
+        assert [x['sum_logpsi'] for x in ea] == [x['sum_logpsi'] for x in eb]
+        a.close(); b.close()
