@@ -626,7 +626,7 @@ def reconstruct_record(args, local, n_prefix=20000, n_general=64):
     eng.set_mps(mps)
     rng = np.random.default_rng(19)
     out = {}
-    imgs = mpslib.synthetic_images(n_prefix, L)
+    imgs = mpslib.synthetic_images(n_prefix, L).astype(np.int64)
     corr = imgs.copy(); corr[:, 392:] = -1
     U = rng.random((392, n_prefix))
     eng.sample(256, U=U[:, :256].copy(), rule='single', prefix=corr[:256], start_site=392)        # warm-up
