@@ -43,7 +43,13 @@ WORKLOADS = {
     'c5': (10000, 784, 128, 384),        # BASELINE config 5 as worded: 4-level pixels as one-hot d=4 sites
     'c5b': (10000, 1568, 128, 768),      # the reference's grayscale notebook: 2 bits per pixel, d stays 2, L doubles
     'tiny': (512, 64, 32, 24),
+    # c3 shape with a Schmidt spectrum decaying over ~10 decades at every cut (stand-in for a trained model): the Gram
+    # split then needs several deflation levels per step; fewer samples, the split is what is measured
+    'c3steep': (8192, 784, 256, 384),
+    'c3steep_lr1e-9': (8192, 784, 256, 384),     # the same with a vanishing learning rate: the update does not lift the tail
 }
+DECADES = {'c3steep': 10.0, 'c3steep_lr1e-9': 10.0}
+LR = {'c3steep_lr1e-9': 1e-9}
 PHYS_DIM = {'c5': 4}
 FP64_PEAK_FALLBACK = 35.7  # cuBLAS DGEMM 8192^3 sustained, measured on this pool in round 1 (profiles/r01_probe_fp64_svd.jsonl);
                            # only used when the live probe below cannot run
@@ -238,7 +244,7 @@ def run_reference(args):
 
 def workload_config(name, world):
     N, L, D, k0 = WORKLOADS[name]
-    return {'workload': f'{name}: synthetic binarized 28x28 (L={L}), {N} samples total, Dmax={D}, '
+    return {'workload': f'{name}: synthetic binarized 28x28 (L={L}), {N} samples total, Dmax={D}, ' + ('Schmidt spectra decaying over ~10 decades, ' if name in DECADES else '') + (f'lr={LR[name]:g}, ' if name in LR else '') +
                         f'mid-chain two-site steps from bond {k0} (full bond dimension), l2 renorm, cutoff 1e-10',
             'n_samples': N, 'sites': L, 'Dmax': D, 'parallelism': f'samples sharded over {world} GPU(s), '
             'one all-reduce of the 2 MiB gradient per step (fused into the split-reduction kernel over NVLink peer memory, or NCCL), replicated SVD' if world > 1 else 'single GPU',
@@ -278,7 +284,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     per = (N + world - 1) // world
     shard = imgs[rank * per:min(N, (rank + 1) * per)]
     start = k0 - warm
-    mps = mpslib.random_mps(L, D, d=d, rng=np.random.default_rng(11), centre=start)
+    mps = mpslib.random_mps(L, D, d=d, rng=np.random.default_rng(11), centre=start, decades=DECADES.get(workload, 0.0))
     eng = BornEngine(L, D, phys_dim=d, device=local, svd=args.svd, precision=args.precision)
     eng.set_data(shard, n_total=N)
     eng.set_mps(mps)
@@ -308,12 +314,13 @@ def measure_steps(args, workload, rank, world, local, full=True):
         return float(t.item())
 
     kw = dict(renorm='l2', max_bond=D, cutoff=1e-10)
+    lr = LR.get(workload, 1e-3)
     k = start
     clocks = ClockSampler(local)
     if rank == 0 and full:
         clocks.start()                    # live before the warm-up: the timed region is shorter than its start-up
     for _ in range(warm):
-        eng.step(k, 1e-3, True, **kw); k += 1
+        eng.step(k, lr, True, **kw); k += 1
 
     trace('warm-up done')
     # ---- timed: EXACTLY `steps` steps, device-resident inputs.  With per-step inputs larger than L2 (N = 1) the K steps
@@ -328,7 +335,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     wall0 = time.perf_counter()
     if flush is None:
         ev[0][0].record()
-        outs = eng.sweep(list(range(k, k + steps)), 1, 1e-3, **kw); k += steps
+        outs = eng.sweep(list(range(k, k + steps)), 1, lr, **kw); k += steps
         ev[0][1].record()
         chis = [o_['chi'] for o_ in outs]
         eng.eig_stats(); levels = [eng.last_gram_levels]
@@ -338,7 +345,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
             flush.fill_(i & 0xff)
             barrier()
             ev[i][0].record()
-            out = eng.step(k, 1e-3, True, **kw); k += 1
+            out = eng.step(k, lr, True, **kw); k += 1
             ev[i][1].record()
             chis.append(out['chi'])
             eng.eig_stats(); levels.append(eng.last_gram_levels)
@@ -357,7 +364,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     if not full:
         eng.set_timing(True)
         for _ in range(3):
-            eng.step(k, 1e-3, True, **kw); k += 1
+            eng.step(k, lr, True, **kw); k += 1
         tim = eng.get_timing(); eng.set_timing(False)
         rec['kernel_ms'] = {n: tim[n][0] / tim[n][1] for n in ('grad', 'psi', 'env_advance', 'merge', 'svd') if tim[n][1]}
         eng.close()
@@ -415,7 +422,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     # ---- per-kernel pass for the roofline (separate, events around each hot launch)
     eng.set_timing(True)
     for _ in range(max(3, min(steps, 8))):
-        eng.step(k, 1e-3, True, **kw); k += 1
+        eng.step(k, lr, True, **kw); k += 1
     tim = eng.get_timing()
     eng.set_timing(False)
     n_loc = shard.shape[0]
@@ -491,7 +498,7 @@ def run_ours(args):
     # ---- the other BASELINE configs that fit one GPU, each as a short run of the same measurement (N=1 only)
     others = {}
     if world == 1 and args.workload == 'c3' and not args.samples and not args.no_others:
-        for w in ('c2', 'c5', 'c5b'):
+        for w in ('c2', 'c5', 'c5b', 'c3steep', 'c3steep_lr1e-9'):
             try:
                 r = measure_steps(args, w, rank, world, local, full=False)
                 others[w] = {'workload': workload_config(w, 1)['workload'], 'ms_per_step': r['ms_per_step'], 'value': r['value'],

@@ -734,7 +734,10 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
     CU(cudaMemcpyAsync(lam_host, c->eLam, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->h_iscal + 2, c->eig_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
+    if (c->h_iscal[2] != 0) {
+      cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream);      // report once: the flag must not fail every later call
+      return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
+    }
     if (c->eig_debug >= 2) {
       long long hp[32];
       CU(cudaMemcpy(hp, c->eProf, sizeof hp, cudaMemcpyDeviceToHost));
@@ -1182,7 +1185,10 @@ static int run_svd_gram_fast(bm_ctx* c, int p, int q, double* iso, double* absb,
       while ((e = cudaEventQuery(c->ev_sync)) == cudaErrorNotReady) {}
       if (e != cudaSuccess) return fail(c, BM_ECUDA, std::string("device error: ") + cudaGetErrorString(e));
     }
-    if (c->h_iscal[2] != 0) return fail(c, BM_ECUDA, "k_sytrd: cluster exchange timed out");
+    if (c->h_iscal[2] != 0) {
+      cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream);      // report once: the flag must not fail every later step
+      return fail(c, BM_ECUDA, "k_sytrd: cluster exchange timed out");
+    }
     dbg_tick(c, "wyT+HOSTWAIT");
     const double* lam = c->h_lam;
     const double lmax = lam[p - 1];
@@ -1447,8 +1453,12 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail
     if (r != BM_OK) return r;
   }
   if (gram && s_host) std::memcpy(s_host, c->h_s.data(), std::min<size_t>(c->h_s.size(), rmin) * sizeof(double));
-  if (c->h_iscal[3] == 1) return fail(c, BM_ECUDA, "k_grad_tf32: mbarrier wait timed out (tcgen05 pipeline)");
-  if (c->h_iscal[3] == 2) return fail(c, BM_ECUDA, "k_grad_reduce_peer: a peer rank did not publish its gradient chunk (flag wait timed out)");
+  if (c->h_iscal[3] != 0) {
+    const int st = c->h_iscal[3];
+    cudaMemsetAsync(c->tf_status, 0, sizeof(int), c->stream);         // report once: the flag must not fail every later step
+    if (st == 1) return fail(c, BM_ECUDA, "k_grad_tf32: mbarrier wait timed out (tcgen05 / TMA pipeline)");
+    return fail(c, BM_ECUDA, "k_grad_reduce_peer: a peer rank did not publish its gradient chunk (flag wait timed out)");
+  }
   if (scalars_host) {
     std::memcpy(scalars_host, c->h_scal, 8 * sizeof(double));
     scalars_host[1] = c->h_scal[8]; scalars_host[2] = c->h_scal[9]; scalars_host[3] = chi;

@@ -135,6 +135,8 @@ class BornEngine:
         t = np.ascontiguousarray(t)
         if t.shape[2] != self.d:
             raise ValueError('physical dimension mismatch')
+        if not np.isfinite(t).all():
+            raise ValueError(f'site tensor {k} holds non-finite entries')
         check(self._ctx, self._lib.bm_set_site(self._ctx, k, _ptr(t), t.shape[0], t.shape[1]))
 
     def set_mps(self, mps):

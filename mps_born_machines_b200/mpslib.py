@@ -41,12 +41,19 @@ def canonize(mps, centre):
     return squeeze_chain(m)
 
 
-def random_mps(L, bond_dim, d=2, rng=None, centre=0):
+def random_mps(L, bond_dim, d=2, rng=None, centre=0, decades=0.0):
     """i.i.d. normal site tensors with every bond = bond_dim (like qtn.MPS_rand_state), canonised to
-    `centre` and normalised (<mps|mps> = |centre tensor|^2 = 1)."""
+    `centre` and normalised (<mps|mps> = |centre tensor|^2 = 1).  decades > 0: the right bond index b of every site is
+    scaled by 10^(-decades * b / bond_dim) first, which gives every cut a Schmidt spectrum decaying over about that many
+    decades (a stand-in for a trained model; a plain random MPS has an almost flat spectrum)."""
     rng = np.random.default_rng(0) if rng is None else rng
     mats = [rng.standard_normal((1 if k == 0 else bond_dim, 1 if k == L - 1 else bond_dim, d)) / np.sqrt(bond_dim * d)
             for k in range(L)]
+    if decades > 0:
+        for k in range(L - 1):
+            w = 10.0 ** (-decades * np.arange(mats[k].shape[1]) / bond_dim)
+            w = w / np.sqrt(np.mean(w * w))                    # unit RMS: the norm of the chain stays O(1) per site
+            mats[k] = mats[k] * w[None, :, None]
     mps = squeeze_chain(mats)
     if centre is not None and 0 <= centre < L:
         mps = canonize(mps, centre)
