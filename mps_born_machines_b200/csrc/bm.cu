@@ -745,6 +745,8 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
       for (int w = 0; w < 3; ++w)
         std::fprintf(stderr, "[bm sytrd_cluster phases, cycles/column, n=%d, warp %d] B %.0f bar %.0f C %.0f bar+copy %.0f wait %.0f D %.0f bar %.0f U %.0f\n", n, w == 0 ? 0 : (w == 1 ? 1 : 15),
                      hp[8 * w] / cols, hp[8 * w + 1] / cols, hp[8 * w + 2] / cols, hp[8 * w + 3] / cols, hp[8 * w + 4] / cols, hp[8 * w + 5] / cols, hp[8 * w + 6] / cols, hp[8 * w + 7] / cols);
+      std::fprintf(stderr, "[bm sytrd_cluster warp-0 phase C, cumulative cycles/column] row sums %.0f p,vr %.0f p.v butterfly %.0f message+fence %.0f\n",
+                   hp[24] / cols, hp[25] / cols, hp[26] / cols, hp[27] / cols);
     }
     if (m > 0) {
       r = eig_wy_factors(c, n);

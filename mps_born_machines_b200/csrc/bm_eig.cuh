@@ -133,7 +133,11 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int me = (int)cluster_ctarank();
   const int g = warp >> 2;                        // row group: local rows 8g .. 8g+7
-  const int cg = ((warp & 3) << 5) | lane;        // column group: columns 4cg .. 4cg+3
+  // column range of the warp: 128 wc .. 128 wc + 127 with (2g + wc) mod 4 = warp mod 4.  The trailing block shrinks to the
+  // warps with large g AND large wc; with wc = warp mod 4 those all sit on the same scheduler (warp mod 4 selects the SM
+  // sub-partition), with this skew the four warps of the last-but-one stage run on four different ones.
+  const int wc = ((warp & 3) - 2 * g) & 3;
+  const int cg = (wc << 5) | lane;                // column group: columns 4cg .. 4cg+3
   double a[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -186,7 +190,8 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
   bool ok = true;
   // PROF: lane 0 of warps 0, 1 and 15 of CTA 0 accumulate the cycles between the marks (phase clocks)
   const bool pr = PROF && prof != nullptr && me == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 15);
-  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0, sub[6] = {0, 0, 0, 0, 0, 0};
+#define SYC_SUB(i) do { if (PROF && pr && warp == 0) { sub[i] += clock64() - tc; } } while (0)
 #define SYC_MARK(i) do { if (PROF && pr) { const long long now_ = clock64(); ph[i] += now_ - tc; tc = now_; } } while (0)
   if (pr) tc = clock64();
   for (int j = 0; j + 2 < n; ++j) {
@@ -201,7 +206,7 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
     }
     // A warp's 64 x 128 tile is dead once all its columns or all its rows are <= j (the trailing block shrinks):
     // dead tiles contribute zeros and are skipped, in the product and in the update (a third of the work on average).
-    const bool live = (128 * (warp & 3) + 127 > j) && (me + EIG_CL * (8 * g + 7) > j);
+    const bool live = (128 * wc + 127 > j) && (me + EIG_CL * (8 * g + 7) > j);
     if (!live) {
       if ((lane & 3) == 0) part[warp][lane >> 2] = 0.0;
     } else {
@@ -238,14 +243,18 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       const int r = me + EIG_CL * lane;
       const int gl = lane >> 3, il = lane & 7;
       const double qs = (part[4 * gl][il] + part[4 * gl + 1][il]) + (part[4 * gl + 2][il] + part[4 * gl + 3][il]);
+      SYC_SUB(0);
       const double p = (r > j && r < n) ? (tj * scale) * fma(-beta, cslice[lane], qs) : 0.0;
       const double vr = (r > j + 1) ? xfull[r] * scale : (r == j + 1 ? 1.0 : 0.0);
+      SYC_SUB(1);
       const double dp = warp_sum(p * vr);
+      SYC_SUB(2);
       sbuf[par][lane] = p;
       sbuf[par][EIG_LR + lane] = cslice[lane];
       if (lane == 0) sbuf[par][2 * EIG_LR] = dp;
       fence_proxy_async_smem();                    // my generic-proxy writes precede the bulk copies issued after the barrier
       if (lane == 0) mbar_expect_tx(eig_smem_u32(&bars[par]), SYTRD_TX_BYTES);
+      SYC_SUB(3);
     }
     const double vt = (t > j + 1) ? x * scale : (t == j + 1 ? 1.0 : 0.0);
     vfull[t] = vt;
@@ -287,21 +296,34 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
       const double2 v23 = *reinterpret_cast<const double2*>(&vfull[4 * cg + 2]);
       const double2 w01 = *reinterpret_cast<const double2*>(&wfull[4 * cg]);
       const double2 w23 = *reinterpret_cast<const double2*>(&wfull[4 * cg + 2]);
+      // Row operands of four rows are loaded together, unconditionally (v and w are exactly zero on finished rows, so
+      // updating them is a no-op): a per-row skip made every row wait for its own two shared-memory loads -- eight
+      // serialised load->FMA chains per column, the longest phase of the kernel (ncu r02: 51 % of the warp samples
+      // between the update barrier and the product barrier).
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = me + EIG_CL * (8 * g + i);
-        if (r <= j) continue;                                  // warp-uniform: finished rows of a partly live tile
-        const double nvs = -vfull[r], nws = -wfull[r];         // two FMAs per element (the FP64 pipe is the busy one)
-        a[i][0] = fma(nvs, w01.x, fma(nws, v01.x, a[i][0]));
-        a[i][1] = fma(nvs, w01.y, fma(nws, v01.y, a[i][1]));
-        a[i][2] = fma(nvs, w23.x, fma(nws, v23.x, a[i][2]));
-        a[i][3] = fma(nvs, w23.y, fma(nws, v23.y, a[i][3]));
+      for (int h = 0; h < 2; ++h) {
+        double nv[4], nw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = me + EIG_CL * (8 * g + 4 * h + i);
+          nv[i] = -vfull[r]; nw[i] = -wfull[r];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ii = 4 * h + i;
+          a[ii][0] = fma(nv[i], w01.x, fma(nw[i], v01.x, a[ii][0]));
+          a[ii][1] = fma(nv[i], w01.y, fma(nw[i], v01.y, a[ii][1]));
+          a[ii][2] = fma(nv[i], w23.x, fma(nw[i], v23.x, a[ii][2]));
+          a[ii][3] = fma(nv[i], w23.y, fma(nw[i], v23.y, a[ii][3]));
+        }
       }
     }
     SYC_MARK(7);                                   // U: (scalars) + rank-2 update
   }
   if (PROF && pr) for (int i = 0; i < 8; ++i) prof[(warp == 0 ? 0 : (warp == 1 ? 8 : 16)) + i] = ph[i];
+  if (PROF && pr && warp == 0) for (int i = 0; i < 6; ++i) prof[24 + i] = sub[i];
 #undef SYC_MARK
+#undef SYC_SUB
   // trailing entries: x is the full column n-2 (n >= 2) or column 0 (n == 1); d[n-2] was stored in phase D (or above)
   if (me == 0 && n >= 2 && t == n - 1) e[n - 2] = x;
 #pragma unroll

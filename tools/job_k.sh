@@ -1,5 +1,5 @@
-BM_EIG_DEBUG=2 python tools/eig_one.py 2>&1 | grep -E "phases" | tail -4
-python tools/test_eig.py 2>/dev/null | python -c "
+BM_EIG_DEBUG=2 timeout 100 python tools/eig_one.py 2>&1 | grep -E "phases|phase C" | tail -4
+timeout 100 python tools/test_eig.py 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     r=json.loads(l)
