@@ -278,12 +278,17 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
     for (int w = EIG_CL / 2; w > 0; w >>= 1)
 #pragma unroll
       for (int c = 0; c < w; ++c) dsum[c] += dsum[c + w];       // fixed tree: a dependent FP64 add costs 23 cycles
+    // everything that does not depend on p.v is formed while the tree of the 16 partial sums is in flight:
+    //   w = p + al2 v,   x' = c - v w[j+1] - w = (c - p - v p[j+1]) - al2 (2 v)          (v[j+1] = 1)
+    const double pt = rbuf[par][t & 15][t >> 4];
+    const double pj1 = rbuf[par][(j + 1) & 15][(j + 1) >> 4];
+    const double base = (rbuf[par][t & 15][EIG_LR + (t >> 4)] - pt) - vt * pj1;
+    const double tv = vt + vt, nhalf_tau = -0.5 * tj;
     const double dot = dsum[0];
-    const double al2 = -0.5 * tj * dot;
-    const double wt = fma(al2, vt, rbuf[par][t & 15][t >> 4]);
-    const double wj1 = rbuf[par][(j + 1) & 15][(j + 1) >> 4] + al2;   // v[j+1] = 1
+    const double al2 = nhalf_tau * dot;
+    const double wt = fma(al2, vt, pt);
     wfull[t] = wt;
-    x = rbuf[par][t & 15][EIG_LR + (t >> 4)] - fma(vt, wj1, wt);      // column j+1 of A - v w^T - w v^T
+    x = fma(-al2, tv, base);                                          // column j+1 of A - v w^T - w v^T
     xfull[t] = (t > j + 1) ? x : 0.0;                                 // published for the next column
     if (me == 0 && t == j + 1) d[j + 1] = x;
     SYC_MARK(5);                                   // D: dot tree, w, next column
