@@ -373,23 +373,24 @@ def measure_steps(args, workload, rank, world, local, full=True):
     trace('timed region done')
     # ---- e2e (a): the reference's own call sequence through the facade with HOST tensors, every step:
     #      learning_step_cached -> write the two tensors back into the host MPS -> sequential_update
-    #      (TNutils.py:1603-1620).  Uploads 4 site tensors and downloads 2 per step (pageable numpy memory, as a
+    #      (TNutils.py:1603-1620).  Uploads the site tensor the engine has not produced itself and downloads 2 per step (pageable numpy memory, as a
     #      notebook user would hold it).
     from mps_born_machines_b200 import TNutils as T
     fmps = T.MPS(eng.get_mps())
     cache = T.ImgCache(eng, shard)
     site_bytes = lambda j: int(fmps.tensors[j].data.nbytes)
     h2d = d2h = 0
+    eng._h2d_bytes = 0
     barrier()
     e0 = time.perf_counter()
     for i in range(steps):
-        h2d += 2 * (site_bytes(k) + site_bytes(k + 1))
-        tn = T.learning_step_cached(fmps, k, None, 1e-3, cache, True, **kw)
+        tn = T.learning_step_cached(fmps, k, None, lr, cache, True, **kw)
         T._write_back(fmps, k, tn)
         T.sequential_update(fmps, None, cache, k, True)
         d2h += site_bytes(k) + site_bytes(k + 1) + 64
         k += 1
     barrier()
+    h2d = eng._h2d_bytes                  # bytes the facade actually uploaded (tensors it handed out itself are not re-sent)
     e2e_value = N * steps / max_over_ranks(time.perf_counter() - e0)
     e2e = {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps, 'd2h_bytes_per_step': d2h // steps,
            'api': 'facade TNutils.learning_step_cached + write-back + sequential_update, host numpy tensors in and out'}

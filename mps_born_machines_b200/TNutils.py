@@ -405,11 +405,31 @@ def _ensure_capacity(mps, img_cache, max_bond, index=None, dims=None):
     return new, True
 
 
+def _same_as_engine(eng, site, data):
+    """True when `data` is (a view of) the read-only array the facade handed out for this site after the engine's last
+    step on it: the device copy is current and the upload can be skipped.  The arrays are flagged read-only when they
+    are handed out, so identity implies unchanged content."""
+    ref = getattr(eng, '_handed_out', {}).get(site)
+    if ref is None:
+        return False
+    base = data
+    while base is not None and base is not ref:
+        base = getattr(base, 'base', None)
+    return base is ref and data.size == ref.size
+
+
+def _upload_site(eng, site, data):
+    if not _same_as_engine(eng, site, data):
+        eng.set_site(site, data)
+        getattr(eng, '_handed_out', {}).pop(site, None)
+        eng._h2d_bytes = getattr(eng, '_h2d_bytes', 0) + int(np.asarray(data).nbytes)
+
+
 def sequential_update(mps, _imgs, img_cache, site, going_right):
     """TNutils.py:504-526: refresh the cache for ALL images after the two tensors at (site, site+1) changed."""
     eng = img_cache.engine
-    eng.set_site(site, mps.tensors[site].data)
-    eng.set_site(site + 1, mps.tensors[site + 1].data)
+    _upload_site(eng, site, mps.tensors[site].data)            # skipped when the tensors are the ones the step just returned
+    _upload_site(eng, site + 1, mps.tensors[site + 1].data)
     eng.env_build(site)
     eng.env_advance(site, going_right)
 
@@ -441,8 +461,8 @@ def computeNLL(mps, imgs, canonicalized_index=False):
 def computeNLL_cached(mps, _imgs, img_cache, index):
     """TNutils.py:892-907: NLL from the cached environments at bond `index`."""
     eng = img_cache.engine
-    eng.set_site(index, mps.tensors[index].data)
-    eng.set_site(index + 1, mps.tensors[index + 1].data)
+    _upload_site(eng, index, mps.tensors[index].data)
+    _upload_site(eng, index + 1, mps.tensors[index + 1].data)
     S = eng.step_grad(index)
     tail = S[-2:].cpu().numpy()
     A = eng.get_merged_at(index)
@@ -463,8 +483,8 @@ def learning_step_cached(mps, index, _imgs, lr, img_cache, going_right=True,
     eng, recreated = _ensure_capacity(mps, img_cache, max_bond, index)
     if recreated:
         eng.env_build(index)
-    eng.set_site(index, mps.tensors[index].data)
-    eng.set_site(index + 1, mps.tensors[index + 1].data)
+    _upload_site(eng, index, mps.tensors[index].data)
+    _upload_site(eng, index + 1, mps.tensors[index + 1].data)
     mask = img_cache.mask
     mom_bias = 0.0
     owner = getattr(update_wrap, '__self__', None)
@@ -484,6 +504,10 @@ def learning_step_cached(mps, index, _imgs, lr, img_cache, going_right=True,
     if out['skipped']:
         print('RIPPERONI')              # the reference's zero-psi message (TNutils.py:1250)
     a, b = eng.get_site(index, squeeze=False), eng.get_site(index + 1, squeeze=False)
+    a.flags.writeable = False; b.flags.writeable = False       # handed out read-only: see _same_as_engine
+    if not hasattr(eng, '_handed_out'):
+        eng._handed_out = {}
+    eng._handed_out[index] = a; eng._handed_out[index + 1] = b
     left = a.transpose(0, 2, 1)          # (Dl,d,chi)
     right = b                            # (chi,Dr,d)
     L = len(mps.tensors)
@@ -559,6 +583,7 @@ def learning_epoch_cached(mps, *args, batch_size=25, update_wrap=None, lr_update
     max_bond, cutoff = kwargs.get('max_bond'), kwargs.get('cutoff', 1e-10)
     eng, _ = _ensure_capacity(mps, img_cache, max_bond)
     eng.set_mps(mps.arrays())
+    eng._handed_out = {}                 # the sweeps below change every site on the device
     eng.env_build(0)
     owner = None
     generic = False

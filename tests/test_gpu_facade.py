@@ -244,3 +244,30 @@ def test_reconstruct_batch_equals_the_per_image_loop(T):
     got = T.reconstruct_batch(mps, corr)
     assert np.array_equal(got, want)
     assert np.array_equal(got[corr != -1], corr[corr != -1]) and set(np.unique(got)) <= {0, 1}
+
+
+def test_step_by_step_uploads_only_foreign_tensors(T):
+    """learning_step_cached + write-back + sequential_update: tensors the facade handed out itself are not uploaded
+    again, anything else (a tensor the user replaced) is; results equal a run that uploads everything."""
+    np.random.seed(31)
+    imgs = (np.random.default_rng(32).random((50, 10)) < 0.4).astype(np.int64)
+    data = np.array([T.tens_picture(img) for img in imgs])
+    start = T.initialize_mps(10, 4)                     # (draws from an unseeded generator: one model for all three runs)
+    def run(perturb, always_upload):
+        mps = start.copy()
+        cache = T.left_right_cache(mps, data, max_bond=8)
+        eng = cache.engine
+        for k in range(0, 6):
+            if always_upload:
+                eng._handed_out = {}
+            tn = T.learning_step_cached(mps, k, data, 0.05, cache, True, max_bond=8, renorm='l2')
+            T._write_back(mps, k, tn)
+            if perturb and k == 2:                       # the user replaces a tensor between the step and the cache update
+                mps.tensors[k + 1].modify(data=mps.tensors[k + 1].data * 1.0)
+            T.sequential_update(mps, data, cache, k, True)
+        return [t.data.copy() for t in mps.tensors], getattr(eng, '_h2d_bytes', 0)
+    a, bytes_a = run(False, False)
+    b, bytes_b = run(False, True)
+    c, bytes_c = run(True, False)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and all(np.array_equal(x, y) for x, y in zip(a, c))
+    assert bytes_a < bytes_c < bytes_b
