@@ -211,6 +211,10 @@ int set_func_attrs(bm_ctx* c) {
   CU(cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradSmem)));
   CU(cudaFuncSetAttribute(k_grad_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradTf32Smem)));
   CU(cudaFuncSetAttribute(k_grad_tf32_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradTmaSmem) + 1024));
+  CU(cudaFuncSetAttribute(k_dgemm<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<64>()));
+  CU(cudaFuncSetAttribute(k_dgemm<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<64>()));
+  CU(cudaFuncSetAttribute(k_dgemm<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<64>()));
+  CU(cudaFuncSetAttribute(k_dgemm<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<64>()));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, c->device));
   c->n_sm = prop.multiProcessorCount;
@@ -238,12 +242,24 @@ int gemm(bm_ctx* c, bool ak, bool bk, int M, int N, int K, double alpha, const d
   auto even64 = [](long long v) { return (v & 1) == 0; };
   P.align16 = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && even64(lda) && even64(ldb) && even64(gb.sAhi) && even64(gb.sAlo) &&
               even64(gb.sBhi) && even64(gb.sBlo) && even64(gb.sAsel) && even64(gb.sBsel);
-  const int tm = (M + GM_T - 1) / GM_T, tn = (N + GM_T - 1) / GM_T;
+  // large batched products (reconstruction) take the 64 x 64 tile, everything on the serial path the 32 x 32 one
+  const bool big = !sym && gb.count >= 8 && M >= 128 && N >= 128;
+  const int T = big ? 64 : GM_T;
+  const int tm = (M + T - 1) / T, tn = (N + T - 1) / T;
   dim3 grid = sym ? dim3(tn * (tn + 1) / 2, 1, gb.count) : dim3(tn, tm, gb.count);
-  if (ak && bk) k_dgemm<true, true><<<grid, GM_THREADS, 0, c->stream>>>(P);
-  else if (ak && !bk) k_dgemm<true, false><<<grid, GM_THREADS, 0, c->stream>>>(P);
-  else if (!ak && !bk) k_dgemm<false, false><<<grid, GM_THREADS, 0, c->stream>>>(P);
-  else k_dgemm<false, true><<<grid, GM_THREADS, 0, c->stream>>>(P);
+  if (big) {
+    const size_t sh = gemm_smem_bytes<64>();
+    if (ak && bk) k_dgemm<64, true, true><<<grid, GM_THREADS, sh, c->stream>>>(P);
+    else if (ak && !bk) k_dgemm<64, true, false><<<grid, GM_THREADS, sh, c->stream>>>(P);
+    else if (!ak && !bk) k_dgemm<64, false, false><<<grid, GM_THREADS, sh, c->stream>>>(P);
+    else k_dgemm<64, false, true><<<grid, GM_THREADS, sh, c->stream>>>(P);
+  } else {
+    const size_t sh = gemm_smem_bytes<32>();
+    if (ak && bk) k_dgemm<32, true, true><<<grid, GM_THREADS, sh, c->stream>>>(P);
+    else if (ak && !bk) k_dgemm<32, true, false><<<grid, GM_THREADS, sh, c->stream>>>(P);
+    else if (!ak && !bk) k_dgemm<32, false, false><<<grid, GM_THREADS, sh, c->stream>>>(P);
+    else k_dgemm<32, false, true><<<grid, GM_THREADS, sh, c->stream>>>(P);
+  }
   c->launches++;
   KCHECK();
   return BM_OK;

@@ -14,13 +14,11 @@
 
 namespace bm {
 
-constexpr int GM_T = 32;             // output tile (GM_T x GM_T)
+constexpr int GM_T = 32;             // output tile of the latency-oriented variant (GM_T x GM_T)
 constexpr int GM_KC = 16;            // k-chunk per stage
 constexpr int GM_STAGES = 3;
-constexpr int GM_THREADS = 128;      // 4 warps, 2 x 2, warp tile 16 x 16
+constexpr int GM_THREADS = 128;      // 4 warps, 2 x 2; warp tile (T/2) x (T/2)
 constexpr int GM_KSTR = GM_KC + 4;   // 20: row stride of a K-major tile  [row][k]   (== 4 mod 16: conflict-free fragments)
-constexpr int GM_MSTR = GM_T + 4;    // 36: row stride of an M-major tile [k][row]
-constexpr int GM_TILE = GM_T * GM_KSTR;   // 640 doubles (>= GM_KC * GM_MSTR = 576)
 
 struct GemmParams {
   const double* A; long long lda;    // A_KMAJOR: A[m*lda + k], else A[k*lda + m]
@@ -38,71 +36,81 @@ struct GemmParams {
   long long sAsel, sBsel;            //   (batched reconstruction: the site matrix of image z's known pixel)
 };
 
-template <bool KMAJOR>
+template <int T> struct GemmTile {
+  static constexpr int MSTR = T + 4;                                   // row stride of an M-major tile [k][row]
+  static constexpr int ELEMS = (T * GM_KSTR > GM_KC * MSTR) ? T * GM_KSTR : GM_KC * MSTR;
+};
+
+template <int T, bool KMAJOR>
 __device__ __forceinline__ void gemm_stage_tile(double* __restrict__ dst, const double* __restrict__ src, long long ld,
                                                 int r0, int R, int k0, int K, int align16) {
   // KMAJOR: dst[row][k] <- src[(r0+row)*ld + k0+k];  else dst[k][row] <- src[(k0+k)*ld + r0+row]
+  constexpr int MSTR = GemmTile<T>::MSTR;
   const int tid = threadIdx.x;
   if (align16) {
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int i = tid + it * GM_THREADS;                 // 256 pieces of 16 bytes
+    for (int it = 0; it < T * GM_KC / 2 / GM_THREADS; ++it) {
+      const int i = tid + it * GM_THREADS;                 // pieces of 16 bytes
       if (KMAJOR) {
         const int row = i >> 3, c2 = (i & 7) * 2;
         const int vr = r0 + row < R ? max(0, min(2, K - k0 - c2)) : 0;
         cp_async16(&dst[row * GM_KSTR + c2], vr ? (const void*)(src + (long long)(r0 + row) * ld + k0 + c2) : (const void*)src, vr * 8);
       } else {
-        const int kk = i >> 4, c2 = (i & 15) * 2;
+        const int kk = i / (T / 2), c2 = (i % (T / 2)) * 2;
         const int vr = k0 + kk < K ? max(0, min(2, R - r0 - c2)) : 0;
-        cp_async16(&dst[kk * GM_MSTR + c2], vr ? (const void*)(src + (long long)(k0 + kk) * ld + r0 + c2) : (const void*)src, vr * 8);
+        cp_async16(&dst[kk * MSTR + c2], vr ? (const void*)(src + (long long)(k0 + kk) * ld + r0 + c2) : (const void*)src, vr * 8);
       }
     }
   } else {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int i = tid + it * GM_THREADS;                 // 512 pieces of 8 bytes
+    for (int it = 0; it < T * GM_KC / GM_THREADS; ++it) {
+      const int i = tid + it * GM_THREADS;                 // pieces of 8 bytes
       if (KMAJOR) {
         const int row = i >> 4, cc = i & 15;
         const bool v = r0 + row < R && k0 + cc < K;
         cp_async8(&dst[row * GM_KSTR + cc], v ? (const void*)(src + (long long)(r0 + row) * ld + k0 + cc) : (const void*)src, v ? 8 : 0);
       } else {
-        const int kk = i >> 5, cc = i & 31;
+        const int kk = i / T, cc = i % T;
         const bool v = k0 + kk < K && r0 + cc < R;
-        cp_async8(&dst[kk * GM_MSTR + cc], v ? (const void*)(src + (long long)(k0 + kk) * ld + r0 + cc) : (const void*)src, v ? 8 : 0);
+        cp_async8(&dst[kk * MSTR + cc], v ? (const void*)(src + (long long)(k0 + kk) * ld + r0 + cc) : (const void*)src, v ? 8 : 0);
       }
     }
   }
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR>
+// T = 32: one small tile per CTA, a 512 x 512 product spreads over the whole chip (serial path: latency).
+// T = 64: warp tile 32 x 32, for the large batched products of the reconstruction (throughput).
+template <int T, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(GM_THREADS) k_dgemm(GemmParams P) {
-  __shared__ __align__(16) double As[GM_STAGES][GM_TILE];
-  __shared__ __align__(16) double Bs[GM_STAGES][GM_TILE];
+  constexpr int MSTR = GemmTile<T>::MSTR, TILE = GemmTile<T>::ELEMS, WT = T / 2, MTN = WT / 8;   // MTN x MTN DMMA tiles per warp
+  extern __shared__ __align__(16) double gm_smem[];
+  double (*As)[TILE] = reinterpret_cast<double (*)[TILE]>(gm_smem);
+  double (*Bs)[TILE] = reinterpret_cast<double (*)[TILE]>(gm_smem + GM_STAGES * TILE);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   int bm_, bn_;
   if (P.sym) {                                   // linear index over the upper triangle of tiles
-    const int nt = (P.N + GM_T - 1) / GM_T;
+    const int nt = (P.N + T - 1) / T;
     int rem = blockIdx.x; bm_ = 0;
     while (rem >= nt - bm_) { rem -= nt - bm_; ++bm_; }
     bn_ = bm_ + rem;
   } else { bm_ = blockIdx.y; bn_ = blockIdx.x; }
-  const int m0 = bm_ * GM_T, n0 = bn_ * GM_T;
+  const int m0 = bm_ * T, n0 = bn_ * T;
   const int zh = blockIdx.z / P.bdiv, zl = blockIdx.z % P.bdiv;
   const int sidx = P.sel ? P.sel[blockIdx.z] : 0;
   const double* __restrict__ A = P.A + zh * P.sAhi + zl * P.sAlo + sidx * P.sAsel;
   const double* __restrict__ B = P.B + zh * P.sBhi + zl * P.sBlo + sidx * P.sBsel;
   const long long coff = zh * P.sChi + zl * P.sClo;
-  double acc[2][2][2];
+  double acc[MTN][MTN][2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < MTN; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < MTN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const int nkc = (P.K + GM_KC - 1) / GM_KC;
 #pragma unroll
   for (int s = 0; s < GM_STAGES - 1; ++s) {
     if (s < nkc) {
-      gemm_stage_tile<A_KMAJOR>(As[s], A, P.lda, m0, P.M, s * GM_KC, P.K, P.align16);
-      gemm_stage_tile<B_KMAJOR>(Bs[s], B, P.ldb, n0, P.N, s * GM_KC, P.K, P.align16);
+      gemm_stage_tile<T, A_KMAJOR>(As[s], A, P.lda, m0, P.M, s * GM_KC, P.K, P.align16);
+      gemm_stage_tile<T, B_KMAJOR>(Bs[s], B, P.ldb, n0, P.N, s * GM_KC, P.K, P.align16);
     }
     cp_async_commit();
   }
@@ -111,29 +119,29 @@ __global__ void __launch_bounds__(GM_THREADS) k_dgemm(GemmParams P) {
     __syncthreads();
     if (it + GM_STAGES - 1 < nkc) {
       const int s = (it + GM_STAGES - 1) % GM_STAGES;
-      gemm_stage_tile<A_KMAJOR>(As[s], A, P.lda, m0, P.M, (it + GM_STAGES - 1) * GM_KC, P.K, P.align16);
-      gemm_stage_tile<B_KMAJOR>(Bs[s], B, P.ldb, n0, P.N, (it + GM_STAGES - 1) * GM_KC, P.K, P.align16);
+      gemm_stage_tile<T, A_KMAJOR>(As[s], A, P.lda, m0, P.M, (it + GM_STAGES - 1) * GM_KC, P.K, P.align16);
+      gemm_stage_tile<T, B_KMAJOR>(Bs[s], B, P.ldb, n0, P.N, (it + GM_STAGES - 1) * GM_KC, P.K, P.align16);
     }
     cp_async_commit();
     const double* as = As[it % GM_STAGES];
     const double* bs = Bs[it % GM_STAGES];
 #pragma unroll
     for (int ks = 0; ks < GM_KC; ks += 4) {
-      double a[2], b[2];
+      double a[MTN], b[MTN];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int row = wm * 16 + mt * 8 + (lane >> 2), kk = ks + (lane & 3);
-        a[mt] = A_KMAJOR ? as[row * GM_KSTR + kk] : as[kk * GM_MSTR + row];
+      for (int mt = 0; mt < MTN; ++mt) {
+        const int row = wm * WT + mt * 8 + (lane >> 2), kk = ks + (lane & 3);
+        a[mt] = A_KMAJOR ? as[row * GM_KSTR + kk] : as[kk * MSTR + row];
       }
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int col = wn * 16 + nt * 8 + (lane >> 2), kk = ks + (lane & 3);
-        b[nt] = B_KMAJOR ? bs[col * GM_KSTR + kk] : bs[kk * GM_MSTR + col];
+      for (int nt = 0; nt < MTN; ++nt) {
+        const int col = wn * WT + nt * 8 + (lane >> 2), kk = ks + (lane & 3);
+        b[nt] = B_KMAJOR ? bs[col * GM_KSTR + kk] : bs[kk * MSTR + col];
       }
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MTN; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < MTN; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
   }
   cp_async_wait<0>();
@@ -141,11 +149,11 @@ __global__ void __launch_bounds__(GM_THREADS) k_dgemm(GemmParams P) {
   const double* __restrict__ Cin = P.Cin ? P.Cin + coff : nullptr;
   double ssq = 0.0;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MTN; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const int row = m0 + wm * 16 + mt * 8 + (lane >> 2);
-      const int col = n0 + wn * 16 + nt * 8 + 2 * (lane & 3);
+    for (int nt = 0; nt < MTN; ++nt) {
+      const int row = m0 + wm * WT + mt * 8 + (lane >> 2);
+      const int col = n0 + wn * WT + nt * 8 + 2 * (lane & 3);
       if (row >= P.M) continue;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(GM_THREADS) k_dgemm(GemmParams P) {
       P.sumsq[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
   }
 }
+template <int T> __host__ inline size_t gemm_smem_bytes() { return (size_t)2 * GM_STAGES * GemmTile<T>::ELEMS * sizeof(double); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // compact-WY factors: H_{j0} H_{j0+1} ... H_{j0+31} = I - V T V^T (V = [v_{j0} ... v_{j0+31}], T upper triangular):
