@@ -90,6 +90,8 @@ struct bm_ctx {
   int eig_ok = 0;            // a 16-CTA cluster can be launched on this device
   double *eD = nullptr, *eE = nullptr, *eTau = nullptr, *eV = nullptr, *eZ = nullptr, *eZn = nullptr,
          *eC = nullptr, *eU2 = nullptr, *eDev = nullptr, *eLam = nullptr, *eGm = nullptr, *eT = nullptr;
+  double* eBt = nullptr;        // trailing block handed from k_sytrd_cluster to k_sytrd_tail
+  int sytrd_tail = 1;           // BM_SYTRD_TAIL=0: the cluster kernel does every column
   long long* eProf = nullptr;   // BM_EIG_DEBUG=2: phase clocks of k_sytrd_cluster
   double* h_dev = nullptr;   // pinned
   int* eig_status = nullptr; // raised by a bounded mbarrier wait of the cluster exchange that timed out
@@ -274,6 +276,13 @@ int gemm(bm_ctx* c, bool ak, bool bk, int M, int N, int K, double alpha, const d
 void dbg_tick(bm_ctx* c, const char* label);
 void dbg_flush(bm_ctx* c);
 
+// Gram split: a level resolves the eigenvalues above GRAM_TAU of its largest (see run_svd_gram_fast)
+// tau = 1e-8: values down to 1e-4 s_0 come from the first level.  Worst-case bound eps n / (2 tau) = 2.8e-6 at n = 512,
+// MEASURED worst error 1.1e-9 on 512 x 512 matrices with random orthogonal factors and log-uniform spectra (6e-11 at
+// tau = 1e-7, 2.9e-10 at 2.5e-8: tools/tau_experiment.py, profiles/r02_tau_experiment.jsonl; the contract is 1e-6), and
+// the c3 bench needs a second level in 2 of 60 steps instead of 7 (BM_GRAM_TAU overrides: experiments).
+double GRAM_TAU = 1e-8;
+
 // ---- on-chip symmetric eigensolver (bm_eig.cuh) -----------------------------------------------------------------
 constexpr int DEV_SLOTS = 16;      // eDev / h_dev: one per Gram level (<= 8), [8] cross-level polish, [9] second round
 constexpr int BM_EIG_UNAVAILABLE = -1;   // internal: cluster launch refused, use cuSOLVER
@@ -295,7 +304,7 @@ int eig_setup(bm_ctx* c) {
   if (ncl < 1) return BM_OK;
   const size_t N = EIG_NMAX;
   DALLOC(c->eD, N); DALLOC(c->eE, N); DALLOC(c->eTau, N); DALLOC(c->eLam, N); DALLOC(c->eZn, N); DALLOC(c->eDev, DEV_SLOTS); DALLOC(c->eU2, N * N); DALLOC(c->eGm, 8 * (N / REFL_CHUNK + 1)); DALLOC(c->eT, (N / WY_B + 1) * WY_B * WY_B);
-  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N); DALLOC(c->eig_status, 1); DALLOC(c->eProf, 32);
+  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N); DALLOC(c->eig_status, 1); DALLOC(c->eProf, 32); DALLOC(c->eBt, (size_t)SYTRD_TAIL_N * SYTRD_TAIL_N);
   CU(cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->eV, 0, N * EIG_LDV * sizeof(double), c->stream));
   CU(cudaFuncSetAttribute(k_tri_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM));
@@ -309,6 +318,8 @@ int eig_setup(bm_ctx* c) {
   c->eig_ok = 1;
   if (const char* dbg = std::getenv("BM_EIG_DEBUG")) c->eig_debug = std::atoi(dbg);
   if (const char* v = std::getenv("BM_SAMPLE_FUSED")) c->sample_fused = std::atoi(v);
+  if (const char* v = std::getenv("BM_SYTRD_TAIL")) c->sytrd_tail = std::atoi(v);
+  if (const char* v = std::getenv("BM_GRAM_TAU")) GRAM_TAU = std::atof(v);
   if (c->eig_debug) for (auto& ev : c->eig_ev) CU(cudaEventCreate(&ev));
   return BM_OK;
 }
@@ -316,12 +327,23 @@ int eig_setup(bm_ctx* c) {
 // eigenvalues of the symmetric n x n matrix G (device, ld) -> c->eLam (device, ascending).  Reflectors stay in eV/eTau.
 int eig_values(bm_ctx* c, const double* G, int ld, int n) {
   if (c->eig_prof) cudaEventRecord(c->eig_ev[0], c->stream);
-  if (c->eig_debug >= 2) k_sytrd_cluster<true><<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status, c->eProf);
-  else k_sytrd_cluster<false><<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status, nullptr);
+  // n <= 128: one CTA does everything (k_sytrd_tail); larger: the cluster kernel up to column n - 128, then the tail
+  const bool tail = c->sytrd_tail && n >= 3;
+  const int jstop = !tail ? n - 2 : (n > SYTRD_TAIL_N ? n - SYTRD_TAIL_N : 0);
+  if (!tail || jstop > 0) {
+    double* bt = tail ? c->eBt : nullptr;
+    if (c->eig_debug >= 2) k_sytrd_cluster<true><<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status, c->eProf, jstop, bt);
+    else k_sytrd_cluster<false><<<EIG_CL, EIG_NT, 0, c->stream>>>(G, ld, n, c->eD, c->eE, c->eTau, c->eV, c->eig_status, nullptr, jstop, bt);
+  }
   if (cudaPeekAtLastError() != cudaSuccess) {      // the cluster cannot be placed after all (e.g. a partitioned GPU):
     cudaGetLastError();                            // stop using the on-chip path, the caller falls back to cuSOLVER
     c->eig_ok = 0;
     return BM_EIG_UNAVAILABLE;
+  }
+  if (tail) {
+    if (jstop > 0) k_sytrd_tail<<<1, 512, 0, c->stream>>>(c->eBt, SYTRD_TAIL_N, n - jstop, jstop, n, c->eD, c->eE, c->eTau, c->eV, EIG_LDV);
+    else k_sytrd_tail<<<1, 512, 0, c->stream>>>(G, ld, n, 0, n, c->eD, c->eE, c->eTau, c->eV, EIG_LDV, c->eig_debug >= 3 ? c->eProf : nullptr);
+    c->launches++;
   }
   if (c->eig_prof) cudaEventRecord(c->eig_ev[1], c->stream);
   dbg_tick(c, "sytrd");
@@ -689,7 +711,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->tfL, c->tfR, c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->tfL, c->tfR, c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eBt, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.rej_list, c->chain.rej_count, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -754,7 +776,15 @@ int bm_eig_sym(bm_ctx* c, int n, const double* G_host, int m, int on_chip, doubl
       cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream);      // report once: the flag must not fail every later call
       return fail(c, BM_ECUDA, "k_sytrd_cluster: cluster exchange timed out");
     }
-    if (c->eig_debug >= 2) {
+    if (c->eig_debug >= 3 && n <= SYTRD_TAIL_N) {
+      long long hp[16];
+      CU(cudaMemcpy(hp, c->eProf, sizeof hp, cudaMemcpyDeviceToHost));
+      const double cols = n > 2 ? n - 2 : 1;
+      for (int w = 0; w < 2; ++w)
+        std::fprintf(stderr, "[bm sytrd_tail phases, cycles/column, n=%d, warp %d] product+reduce %.0f wait scalars %.0f p,dp %.0f bar %.0f D %.0f bar %.0f U(+scalars) %.0f\n", n, w ? 15 : 0,
+                     hp[8 * w] / cols, hp[8 * w + 1] / cols, hp[8 * w + 2] / cols, hp[8 * w + 3] / cols, hp[8 * w + 4] / cols, hp[8 * w + 5] / cols, hp[8 * w + 6] / cols);
+    }
+    if (c->eig_debug == 2) {
       long long hp[32];
       CU(cudaMemcpy(hp, c->eProf, sizeof hp, cudaMemcpyDeviceToHost));
       const double cols = n > 2 ? n - 2 : 1;
@@ -1165,7 +1195,6 @@ static int chi_rule(const std::vector<double>& sv, double cutoff, int max_bond) 
 // the relative cutoff rule (1e-10) exact.
 //   c->W holds Y = (q x p, column-major): A^T when the left factor is the isometry (p = mA), A otherwise (p = nA).
 //   Outputs: isometry (p x chi) and absorbed factor (q x chi) in c->U / c->V, singular values in c->h_s, chi.
-constexpr double GRAM_TAU = 1e-7;   // level-0 values down to 3e-4 s_0: rel. error <= eps*n/(2 tau) ~ 2.5e-7
 
 // ---- fast path: on-chip eigensolver (bm_eig.cuh).  A level resolves the eigenvalues above TAU of its largest; the
 // resolved directions are then projected out of Y (Y <- Y - (Y U) U^T, on Y so that the small singular values keep

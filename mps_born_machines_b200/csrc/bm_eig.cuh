@@ -116,12 +116,14 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity)
 //   U   warps 1..15: rank-2 update of the register block.  Warp 0 FIRST computes the norm and the Householder scalars
 //       of the NEXT column from xfull (one butterfly; while the other warps are in their FP64-bound update the queue
 //       is free -- in phase B the same chain took 1900 cycles behind the other warps' shuffles), then its update.
+constexpr int SYTRD_TAIL_N = 128;                             // the last 128 columns run in one CTA (k_sytrd_tail)
 constexpr int SYTRD_MSG = 2 * EIG_LR + 2;                     // p[32], column slice[32], p.v, pad -> 528 bytes
 constexpr uint32_t SYTRD_TX_BYTES = EIG_CL * SYTRD_MSG * 8;
 template <bool PROF>
 __global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_NT, 1)
 k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict__ d, double* __restrict__ e,
-                double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status, long long* __restrict__ prof) {
+                double* __restrict__ tau, double* __restrict__ V, int* __restrict__ status, long long* __restrict__ prof,
+                int jstop, double* __restrict__ Btail) {
   __shared__ __align__(16) double vfull[EIG_NMAX], wfull[EIG_NMAX];
   __shared__ __align__(16) double rbuf[2][EIG_CL][SYTRD_MSG];   // received messages, one per source CTA
   __shared__ __align__(16) double sbuf[2][SYTRD_MSG];           // my outgoing message
@@ -194,7 +196,9 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
 #define SYC_SUB(i) do { if (PROF && pr && warp == 0) { sub[i] += clock64() - tc; } } while (0)
 #define SYC_MARK(i) do { if (PROF && pr) { const long long now_ = clock64(); ph[i] += now_ - tc; tc = now_; } } while (0)
   if (pr) tc = clock64();
-  for (int j = 0; j + 2 < n; ++j) {
+  // columns 0 .. jstop-1 here; the trailing (n - jstop)^2 block is handed to the single-CTA kernel k_sytrd_tail
+  // (jstop = n - 2 and Btail = nullptr: everything here)
+  for (int j = 0; j < jstop; ++j) {
     const int par = j & 1;
     // ---- B: my 8 entries of the not-yet-updated column j+1;  q = A xh on my rows (does not need the scalars:
     //         A v = scale (A xh - beta A[:, j+1]))
@@ -295,7 +299,7 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
     __syncthreads();
     SYC_MARK(6);                                   // barrier
     // ---- U: (warp 0: norm + scalars of the next column first) rank-2 update of my block
-    if (warp == 0 && j + 3 < n) scalars_for(j + 1);
+    if (warp == 0 && j + 1 < jstop) scalars_for(j + 1);
     if (live && 4 * cg + 3 > j) {
       const double2 v01 = *reinterpret_cast<const double2*>(&vfull[4 * cg]);
       const double2 v23 = *reinterpret_cast<const double2*>(&vfull[4 * cg + 2]);
@@ -329,17 +333,207 @@ k_sytrd_cluster(const double* __restrict__ G, int ld, int n, double* __restrict_
   if (PROF && pr && warp == 0) for (int i = 0; i < 6; ++i) prof[24 + i] = sub[i];
 #undef SYC_MARK
 #undef SYC_SUB
-  // trailing entries: x is the full column n-2 (n >= 2) or column 0 (n == 1); d[n-2] was stored in phase D (or above)
-  if (me == 0 && n >= 2 && t == n - 1) e[n - 2] = x;
+  if (Btail) {
+    // hand-over: the trailing block (rows and columns >= jstop, all updates applied) goes to global memory, row-major
+    // with leading dimension SYTRD_TAIL_N; the tail kernel continues with it as a fresh problem
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = me + EIG_CL * (8 * g + i);
+    for (int i = 0; i < 8; ++i) {
+      const int r = me + EIG_CL * (8 * g + i);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (n >= 2 && r == n - 1 && 4 * cg + k == n - 1) d[n - 1] = a[i][k];
+      for (int k = 0; k < 4; ++k) {
+        const int cidx = 4 * cg + k;
+        if (r >= jstop && r < n && cidx >= jstop && cidx < n) Btail[(size_t)(r - jstop) * SYTRD_TAIL_N + (cidx - jstop)] = a[i][k];
+      }
+    }
+  } else {
+    // trailing entries: x is the full column n-2 (n >= 2) or column 0 (n == 1); d[n-2] was stored in phase D (or above)
+    if (me == 0 && n >= 2 && t == n - 1) e[n - 2] = x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = me + EIG_CL * (8 * g + i);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (n >= 2 && r == n - 1 && 4 * cg + k == n - 1) d[n - 1] = a[i][k];
+    }
   }
   if (!ok && t == 0) atomicExch(status, 3);
   cluster_sync_all();                             // nobody exits while a peer could still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_sytrd_tail — the same Householder tridiagonalisation for m <= 128 inside ONE CTA (no cluster, no exchange): a column
+// of the cluster kernel costs ~3900 cycles whatever the size of the trailing block (exchange flight, cluster-wide
+// chain), so its last 128 columns -- and every problem with n <= 128 -- run here at ~1/3 of that.
+//   B: symmetric m x m (row-major, ldb), global rows/columns off .. off+m-1 of the original problem.  Writes d[off+i],
+//   e[off+i], tau[off+i] and the reflectors V[(off+i)*ldv + r] (all nfull entries of a row, zeros outside the block).
+// Thread (w, l): rows 8w..8w+7, columns 4l..4l+3 of the block in registers: a warp holds 8 COMPLETE rows, so the row sums
+// of A xh come out of the in-warp transpose-reduce and p, p.v are formed without a CTA barrier.  Warp 0 (its rows are
+// finished after 8 columns) computes the norm and Householder scalars of the next column during the update phase and
+// publishes them through a named hardware barrier.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+k_sytrd_tail(const double* __restrict__ B, int ldb, int m, int off, int nfull, double* __restrict__ d, double* __restrict__ e,
+             double* __restrict__ tau, double* __restrict__ V, int ldv, long long* __restrict__ prof = nullptr) {
+  constexpr int TN = SYTRD_TAIL_N;
+  __shared__ __align__(16) double xs[TN], vs[TN], ws[TN], cs[TN], ps[TN];
+  __shared__ double dpart[16];
+  __shared__ double scl[4];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  double a[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 8 * w + i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 4 * lane + k;
+      a[i][k] = (r < m && c < m) ? B[(size_t)r * ldb + c] : 0.0;
+    }
+  }
+  if (t < TN) xs[t] = (t > 0 && t < m) ? B[(size_t)t * ldb] : 0.0;      // column 0, masked (B symmetric)
+  if (t == 0) d[off] = B[0];
+  __syncthreads();
+  // norm + scalars of block column jc from xs (zero on rows <= jc): one warp, one butterfly
+  auto scalars_for = [&](int jc) {
+    const double4 u = *reinterpret_cast<const double4*>(&xs[4 * lane]);
+    const int e0 = 4 * lane;
+    double s0 = (e0 == jc + 1 ? 0.0 : u.x) * u.x, s1 = (e0 + 1 == jc + 1 ? 0.0 : u.y) * u.y;
+    s0 = fma(e0 + 2 == jc + 1 ? 0.0 : u.z, u.z, s0); s1 = fma(e0 + 3 == jc + 1 ? 0.0 : u.w, u.w, s1);
+    const double xn2 = warp_sum(s0 + s1);
+    const double alpha = xs[jc + 1];
+    double beta = alpha, tj = 0.0, scale = 0.0;
+    if (xn2 != 0.0) {
+      const double nn = fma(alpha, alpha, xn2);
+      const double rinv = fast_rsqrt(nn);
+      beta = -copysign(nn * rinv, alpha);
+      tj = (beta - alpha) * (-copysign(rinv, alpha));
+      scale = fast_rcp(alpha - beta);
+    }
+    if (lane == 0) { scl[0] = beta; scl[1] = tj; scl[2] = scale; }
+  };
+  if (w == 0 && m > 2) scalars_for(0);
+  __syncthreads();
+  const bool pr = prof != nullptr && lane == 0 && (w == 0 || w == 15);
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = pr ? clock64() : 0;
+#define TL_MARK(i) do { if (pr) { const long long now_ = clock64(); ph[i] += now_ - tc; tc = now_; } } while (0)
+  for (int j = 0; j + 2 < m; ++j) {
+    // ---- B: column j+1 of my rows, q = A xh, row sums inside the warp, then p and the partial p.v
+    {
+      const int kk = (j + 1) & 3;
+      if (lane == ((j + 1) >> 2)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs[8 * w + i] = kk == 0 ? a[i][0] : (kk == 1 ? a[i][1] : (kk == 2 ? a[i][2] : a[i][3]));
+      }
+    }
+    const bool live = 8 * w + 7 > j;             // warp-uniform: my rows are not all finished
+    double pmine = 0.0, dp = 0.0;
+    int rmine = 0;
+    if (live) {
+      const double4 xv = *reinterpret_cast<const double4*>(&xs[4 * lane]);
+      double q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fma(a[i][0], xv.x, fma(a[i][1], xv.y, fma(a[i][2], xv.z, a[i][3] * xv.w)));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double send = (lane & 16) ? q[k] : q[k + 4], keep = (lane & 16) ? q[k + 4] : q[k];
+        q[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double send = (lane & 8) ? q[k] : q[k + 2], keep = (lane & 8) ? q[k + 2] : q[k];
+        q[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const double send = (lane & 4) ? q[0] : q[1], keep = (lane & 4) ? q[1] : q[0];
+        q[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      q[0] += __shfl_xor_sync(0xffffffffu, q[0], 2);
+      q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+      TL_MARK(0);                                 // product + transpose-reduce
+      __syncwarp();                               // cs of my rows (written by one lane of this warp) is visible
+      // scalars of column j: written by warp 0 during the previous update phase.  Hardware barrier 1 (every warp arrives
+      // once per column: warp 0 after writing them, finished warps at once, live warps wait here) -- polling a flag in
+      // shared memory from 15 warps slowed warp 0's own chain down.
+      if (j > 0 && w != 0) asm volatile("bar.sync 1, 512;" ::: "memory");
+      TL_MARK(1);                                 // wait for the scalars
+      const double beta = scl[0], tj = scl[1], scale = scl[2];
+      rmine = 8 * w + (lane >> 2);                // lanes 0, 4, ..., 28 hold the sum of local row lane >> 2
+      if ((lane & 3) == 0 && rmine > j && rmine < m) {
+        pmine = (tj * scale) * fma(-beta, cs[rmine], q[0]);
+        const double vr = (rmine > j + 1) ? xs[rmine] * scale : 1.0;      // rmine == j+1: v = 1
+        dp = pmine * vr;
+      }
+      dp += __shfl_xor_sync(0xffffffffu, dp, 16);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 8);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 4);
+      if ((lane & 3) == 0) ps[rmine] = pmine;
+    } else {
+      if (j > 0 && w != 0) asm volatile("bar.arrive 1, 512;" ::: "memory");
+      if ((lane & 3) == 0) ps[8 * w + (lane >> 2)] = 0.0;
+    }
+    if (lane == 0) dpart[w] = dp;
+    TL_MARK(2);                                   // p, partial p.v
+    __syncthreads();
+    TL_MARK(3);                                   // barrier
+    // ---- D: p.v, w, element t of the next column (threads 0 .. 127)
+    const double beta = scl[0], tj = scl[1], scale = scl[2];
+    if (t < TN) {
+      double ds[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) ds[c] = dpart[c];
+      const double pt = ps[t], pj1 = ps[j + 1];
+      const double vt = (t > j + 1 && t < m) ? xs[t] * scale : (t == j + 1 ? 1.0 : 0.0);
+      const double base = (cs[t] - pt) - vt * pj1;
+      const double tv = vt + vt, nhalf_tau = -0.5 * tj;
+#pragma unroll
+      for (int q2 = 8; q2 > 0; q2 >>= 1)
+#pragma unroll
+        for (int c = 0; c < q2; ++c) ds[c] += ds[c + q2];
+      const double al2 = nhalf_tau * ds[0];
+      const double wt = fma(al2, vt, pt);
+      const double xn = fma(-al2, tv, base);
+      vs[t] = vt; ws[t] = wt;
+      xs[t] = (t > j + 1 && t < m) ? xn : 0.0;
+      if (t == j + 1) d[off + j + 1] = xn;
+      if (t == 0) { e[off + j] = beta; tau[off + j] = tj; }
+    }
+    TL_MARK(4);                                   // D
+    __syncthreads();
+    TL_MARK(5);                                   // barrier
+    // ---- U: (warp 0: scalars of the next column) reflector store, rank-2 update
+    if (w == 0 && j + 3 < m) {
+      scalars_for(j + 1);
+      asm volatile("bar.arrive 1, 512;" ::: "memory");      // (bar.arrive orders my shared-memory writes before the waiters' reads)
+    }
+    V[(size_t)(off + j) * ldv + t] = (t >= off && t < off + TN) ? vs[t - off] : 0.0;    // all 512 entries of the row
+    if (live && 4 * lane + 3 > j) {
+      const double4 vv = *reinterpret_cast<const double4*>(&vs[4 * lane]);
+      const double4 wv = *reinterpret_cast<const double4*>(&ws[4 * lane]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double nv[4], nw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { nv[i] = -vs[8 * w + 4 * h + i]; nw[i] = -ws[8 * w + 4 * h + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ii = 4 * h + i;
+          a[ii][0] = fma(nv[i], wv.x, fma(nw[i], vv.x, a[ii][0]));
+          a[ii][1] = fma(nv[i], wv.y, fma(nw[i], vv.y, a[ii][1]));
+          a[ii][2] = fma(nv[i], wv.z, fma(nw[i], vv.z, a[ii][2]));
+          a[ii][3] = fma(nv[i], wv.w, fma(nw[i], vv.w, a[ii][3]));
+        }
+      }
+    }
+    TL_MARK(6);                                   // U (+ scalars in warp 0)
+  }
+  if (pr) for (int i = 0; i < 8; ++i) prof[(w == 0 ? 0 : 8) + i] = ph[i];
+#undef TL_MARK
+  // trailing entries: xs holds block column m-2 (masked); element (m-1, m-1) is in the registers
+  if (m >= 2 && t == m - 1) e[off + m - 2] = (m == 2) ? B[(size_t)1 * ldb] : xs[m - 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (m >= 2 && 8 * w + i == m - 1 && 4 * lane + k == m - 1) d[off + m - 1] = a[i][k];
 }
 
 // ------------------------------------------------------------------------------------------------------------------

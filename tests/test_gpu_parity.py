@@ -800,3 +800,27 @@ def test_sweep_call_equals_step_by_step(bm):
         ea = a.epoch(0.05, 'l2', max_bond=D); eb = [b.step(k, 0.05, bool(dirs[i]), 'l2', max_bond=D) for i, k in enumerate(bonds)]
         assert [x['sum_logpsi'] for x in ea] == [x['sum_logpsi'] for x in eb]
         a.close(); b.close()
+
+
+def test_gram_split_accuracy_near_the_level_threshold(bm):
+    """512 x 512 merged tensors with random orthogonal factors and a log-uniform spectrum whose 256th value sits around
+    1e-4 s_0 -- the region where the first Gram level hands over to the second (tau = 1e-8 in lambda = 1e-4 in sigma):
+    every kept singular value within 1e-8 relative of the known spectrum (measured ~1e-9; the contract is 1e-6)."""
+    D = 256
+    for seed, lo in ((0, 1e-8), (1, 3e-9)):
+        rng = np.random.default_rng(900 + seed)
+        s = np.sort(np.exp(rng.uniform(np.log(lo), 0.0, size=2 * D)))[::-1]; s[0] = 1.0
+        U, _ = np.linalg.qr(rng.standard_normal((2 * D, 2 * D)))
+        V, _ = np.linalg.qr(rng.standard_normal((2 * D, 2 * D)))
+        m1 = (U * s).reshape(D, 2, 2 * D).transpose(0, 2, 1)
+        m2 = V.T.reshape(2 * D, D, 2)
+        mps = [rng.standard_normal((D, 2)), m1, m2, rng.standard_normal((D, 2))]
+        eng = bm.BornEngine(4, 2 * D)
+        for gr in (True, False):
+            eng.set_mps(mps)
+            out = eng.split_bond(1, going_right=gr, max_bond=D, cutoff=1e-10, want_s=True)
+            assert out['chi'] == D
+            rel = np.abs(out['s'] - s[:D]) / s[:D]
+            assert rel.max() < 1e-8, (seed, gr, rel.max(), s[int(rel.argmax())])
+        assert eng.eig_stats()[1] == 0
+        eng.close()
