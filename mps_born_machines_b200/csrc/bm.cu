@@ -98,6 +98,8 @@ struct bm_ctx {
   long long eig_fast = 0, eig_fallback = 0;
   long long fb_reason[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // why a split left the on-chip path (bm_eig_fallback_reasons)
   double last_pred = 0.0;
+  int refine_lo = 0, refine_hi = 0;   // singular values [lo, hi) of the last split are Rayleigh quotients (row norms of the absorbed factor)
+  double* eRn = nullptr; double* h_rn = nullptr;
   int two_round[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // level used a second Newton-Schulz round (close eigenvalues)
   int trivec3 = 1;              // 1: k_tri_vectors3 (three-term pivots), 0: k_tri_vectors (qd form; BM_TRIVEC=qd)
   int wy_back = 1;              // 1: blocked compact-WY back-transformation (k_wy_T + k_wy_apply), 0: k_apply_reflectors (BM_BACKTRANSFORM=warp)
@@ -282,6 +284,11 @@ void dbg_flush(bm_ctx* c);
 // tau = 1e-7, 2.9e-10 at 2.5e-8: tools/tau_experiment.py, profiles/r02_tau_experiment.jsonl; the contract is 1e-6), and
 // the c3 bench needs a second level in 2 of 60 steps instead of 7 (BM_GRAM_TAU overrides: experiments).
 double GRAM_TAU = 1e-8;
+// Values between GRAM_TAU2 and GRAM_TAU of the level's largest (1e-4 .. 3e-6 of its largest singular value) are weakly
+// resolved as eigenvalues but their eigenvectors are still good to ~eps/ratio: when they are all that is missing to reach
+// max_bond they are taken in the same level, with the singular value recomputed as the norm of the projected row
+// (Rayleigh quotient) instead of a second full eigen-decomposition.
+double GRAM_TAU2 = 1e-11;
 
 // ---- on-chip symmetric eigensolver (bm_eig.cuh) -----------------------------------------------------------------
 constexpr int DEV_SLOTS = 16;      // eDev / h_dev: one per Gram level (<= 8), [8] cross-level polish, [9] second round
@@ -304,7 +311,8 @@ int eig_setup(bm_ctx* c) {
   if (ncl < 1) return BM_OK;
   const size_t N = EIG_NMAX;
   DALLOC(c->eD, N); DALLOC(c->eE, N); DALLOC(c->eTau, N); DALLOC(c->eLam, N); DALLOC(c->eZn, N); DALLOC(c->eDev, DEV_SLOTS); DALLOC(c->eU2, N * N); DALLOC(c->eGm, 8 * (N / REFL_CHUNK + 1)); DALLOC(c->eT, (N / WY_B + 1) * WY_B * WY_B);
-  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N); DALLOC(c->eig_status, 1); DALLOC(c->eProf, 32); DALLOC(c->eBt, (size_t)SYTRD_TAIL_N * SYTRD_TAIL_N);
+  DALLOC(c->eV, N * EIG_LDV); DALLOC(c->eZ, N * N); DALLOC(c->eC, N * N); DALLOC(c->eig_status, 1); DALLOC(c->eProf, 32); DALLOC(c->eBt, (size_t)SYTRD_TAIL_N * SYTRD_TAIL_N); DALLOC(c->eRn, N);
+  CU(cudaMallocHost((void**)&c->h_rn, N * sizeof(double)));
   CU(cudaMemsetAsync(c->eig_status, 0, sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->eV, 0, N * EIG_LDV * sizeof(double), c->stream));
   CU(cudaFuncSetAttribute(k_tri_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM));
@@ -320,6 +328,7 @@ int eig_setup(bm_ctx* c) {
   if (const char* v = std::getenv("BM_SAMPLE_FUSED")) c->sample_fused = std::atoi(v);
   if (const char* v = std::getenv("BM_SYTRD_TAIL")) c->sytrd_tail = std::atoi(v);
   if (const char* v = std::getenv("BM_GRAM_TAU")) GRAM_TAU = std::atof(v);
+  if (const char* v = std::getenv("BM_GRAM_TAU2")) GRAM_TAU2 = std::atof(v);
   if (c->eig_debug) for (auto& ev : c->eig_ev) CU(cudaEventCreate(&ev));
   return BM_OK;
 }
@@ -711,7 +720,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
-                  c->tfL, c->tfR, c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eBt, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
+                  c->tfL, c->tfR, c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eBt, c->eRn, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
                   c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.rej_list, c->chain.rej_count, c->chain.U, c->chain.lnabs, c->chain.sign};
@@ -720,6 +729,7 @@ int bm_destroy(bm_ctx* c) {
   if (c->h_iscal) cudaFreeHost(c->h_iscal);
   if (c->h_lam) cudaFreeHost(c->h_lam);
   if (c->h_dev) cudaFreeHost(c->h_dev);
+  if (c->h_rn) cudaFreeHost(c->h_rn);
   for (auto& ev : c->eig_ev) if (ev) cudaEventDestroy(ev);
   for (auto& tk : c->dbg_ticks) cudaEventDestroy(tk.second);
   if (c->tev[0]) { cudaEventDestroy(c->tev[0]); cudaEventDestroy(c->tev[1]); }
@@ -1213,6 +1223,7 @@ static int run_svd_gram_fast(bm_ctx* c, int p, int q, double* iso, double* absb,
   double sigma0sq = 0.0;
   CU(cudaMemsetAsync(c->eDev, 0, DEV_SLOTS * sizeof(double), c->stream));
   for (int i = 0; i < 8; ++i) c->two_round[i] = 0;
+  c->refine_lo = c->refine_hi = 0;
   while (!finished) {
     ++flev;
     dbg_tick(c, "[level");
@@ -1250,7 +1261,11 @@ static int run_svd_gram_fast(bm_ctx* c, int p, int q, double* iso, double* absb,
     int kkeep = 0;
     if (lmax > 0.0) while (kkeep < peff && lam[p - 1 - kkeep] > GRAM_TAU * lmax) ++kkeep;
     const int rest = peff - kkeep;
-    const bool done = (ncols + kkeep >= need) || rest == 0 || !(lmax > 0.0) || (GRAM_TAU * lmax <= cutoff * cutoff * sigma0sq);
+    const bool done_strict = (ncols + kkeep >= need) || rest == 0 || !(lmax > 0.0) || (GRAM_TAU * lmax <= cutoff * cutoff * sigma0sq);
+    int kext = kkeep;                                        // + weakly resolved values, enough of them to reach `need`
+    if (!done_strict) while (kext < peff && lam[p - 1 - kext] > GRAM_TAU2 * lmax) ++kext;
+    const bool done_ext = !done_strict && (ncols + kext >= need);
+    const bool done = done_strict || done_ext;
     if (!done && flev >= 8) { c->fb_reason[3]++; return BM_OK; }
     const int npush = done ? peff : kkeep;
     for (int j = 0; j < npush; ++j) sv.push_back(std::sqrt(std::max(lam[p - 1 - j], 0.0)));
@@ -1259,8 +1274,9 @@ static int run_svd_gram_fast(bm_ctx* c, int p, int q, double* iso, double* absb,
       if ((int)sv.size() > rmin) sv.resize(rmin);
       chi = chi_rule(sv, cutoff, max_bond);
       nv = chi - ncols;
-      if (nv > kkeep) { c->fb_reason[4]++; return BM_OK; }    // would need vectors of unresolved values
+      if (nv > (done_ext ? kext : kkeep)) { c->fb_reason[4]++; return BM_OK; }    // would need vectors of unresolved values
       if (nv < 0) nv = 0;
+      if (done_ext && nv > kkeep) { c->refine_lo = ncols + kkeep; c->refine_hi = chi; }
     }
     if (nv > 0) {
       // separation of the wanted eigenvalues (and of the last one from its lower neighbour)
@@ -1309,6 +1325,12 @@ static int run_svd_gram_fast(bm_ctx* c, int p, int q, double* iso, double* absb,
   *chi_out = chi; *trunc_out = std::sqrt(t2);
   GEMM(true, false, chi, q, p, 1.0, iso, p, c->W, q, 0.0, nullptr, absb, q);   // absorbed^T = iso^T Y^T (row-major chi x q)
   dbg_tick(c, "project");
+  if (c->refine_hi > c->refine_lo) {                         // Rayleigh quotients of the weakly resolved directions
+    const int nr = c->refine_hi - c->refine_lo;
+    k_row_norms<<<(nr + 7) / 8, 256, 0, c->stream>>>(absb + (size_t)c->refine_lo * q, q, q, nr, c->eRn);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_rn, c->eRn, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaMemcpyAsync(c->h_dev, c->eDev, DEV_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   *ok_out = true;
   return BM_OK;
@@ -1481,6 +1503,7 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail
     if (gram_fast_verified(c)) c->eig_fast++;
     else {                          // rare: the eigenvectors were not orthonormal enough -> cuSOLVER levels from the intact W
       c->eig_fallback++; c->fb_reason[6]++;
+      c->refine_lo = c->refine_hi = 0;
       if (c->eig_debug) std::fprintf(stderr, "[bm split] orthonormality check failed at bond %d: levels %d, measured deviations %.2e %.2e %.2e | second rounds %.2e %.2e | cross-level %.2e, predicted (level 1) %.2e\n",
                                      k, c->gram_levels, c->h_dev[0], c->h_dev[1], c->h_dev[2], c->h_dev[10], c->h_dev[11], c->h_dev[8], c->last_pred);
       r = run_svd_gram_syevd(c, p, q, iso, absb, need, rmin, max_bond, cutoff, &chi, &trunc);
@@ -1499,6 +1522,8 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail
     r = do_advance();
     if (r != BM_OK) return r;
   }
+  if (gram && fast && c->refine_hi > c->refine_lo)            // (the copy was complete at the WAIT above)
+    for (int i = c->refine_lo; i < c->refine_hi && i < (int)c->h_s.size(); ++i) c->h_s[i] = c->h_rn[i - c->refine_lo];
   if (gram && s_host) std::memcpy(s_host, c->h_s.data(), std::min<size_t>(c->h_s.size(), rmin) * sizeof(double));
   if (c->h_iscal[3] != 0) {
     const int st = c->h_iscal[3];

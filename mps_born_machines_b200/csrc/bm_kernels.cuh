@@ -1631,6 +1631,22 @@ __global__ void k_finish_logpsi(const double* __restrict__ E, int ld, const int*
   sign[i] = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
 }
 
+// out[i] = || row i of M ||_2 (M row-major, ld): one warp per row.  The singular values of weakly resolved directions are
+// taken as the norms of the projected rows (Rayleigh quotients: second-order accurate in the eigenvector error).
+__global__ void __launch_bounds__(256) k_row_norms(const double* __restrict__ M, int ld, int ncol, int nrow, double* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= nrow) return;
+  const double* r = M + (long long)row * ld;
+  double s0 = 0.0, s1 = 0.0;
+  int c = lane;
+  for (; c + 32 < ncol; c += 64) { s0 = fma(r[c], r[c], s0); s1 = fma(r[c + 32], r[c + 32], s1); }
+  if (c < ncol) s0 = fma(r[c], r[c], s0);
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = sqrt(s);
+}
+
 // A[i][i] = 1 + i/n (distinct diagonal: warm-up input of the cuSOLVER fallback)
 __global__ void k_set_diag(double* __restrict__ A, int n, int ld) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
