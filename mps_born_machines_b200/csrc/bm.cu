@@ -206,7 +206,7 @@ int ensure_stage(bm_ctx* c, size_t count) {
   return BM_OK;
 }
 
-constexpr size_t PANEL_SMEM = sizeof(PanelSmem<64>);
+constexpr size_t PANEL_SMEM = sizeof(PanelSmem<BM_TM128 ? 128 : 64>);
 
 int set_func_attrs(bm_ctx* c) {
   CU(cudaFuncSetAttribute(k_env_advance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));

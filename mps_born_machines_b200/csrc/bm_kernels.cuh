@@ -38,6 +38,9 @@ constexpr int NTHREADS = 256;   // 8 warps arranged 2 (rows) x 4 (cols)
 #ifndef BM_PSI_BATCH
 #define BM_PSI_BATCH 1
 #endif
+#ifndef BM_TM128
+#define BM_TM128 0      // tuning variant: 128-row tiles in k_env_advance / k_psi (needs BM_MINBLOCKS=1, BM_STAGES=3)
+#endif
 #ifndef BM_NOEPI
 #define BM_NOEPI 0      // tuning only: skip epilogue memory traffic
 #endif
@@ -157,7 +160,7 @@ __device__ __forceinline__ bool locate_tile(const GroupSpec& gs, int& g, int& ro
 // Persistent, balanced tile scheduling.  Work is cut into units of 16 rows (never straddling a group); CTA c of P
 // owns units [c*U/P, (c+1)*U/P) and walks them in tiles of 64 / 32 / 16 rows, so every CTA gets the same work to
 // within one unit (a plain grid of 64-row tiles leaves a 3.18-wave tail at N = 60 000: -20 %).
-template <class F>
+template <int TMAX = 64, class F>
 __device__ __forceinline__ void for_each_tile(const int* __restrict__ goff, int ngroups, F&& f) {
   long long U = 0;
   for (int g = 0; g < ngroups; ++g) U += (goff[g + 1] - goff[g] + UNIT - 1) / UNIT;
@@ -172,7 +175,7 @@ __device__ __forceinline__ void for_each_tile(const int* __restrict__ goff, int 
       const int rend = min(ge, gb + (int)(hi - acc) * UNIT);
       while (row < rend) {
         const int rem = rend - row;
-        const int tm = rem > 32 ? 64 : (rem > 16 ? 32 : 16);
+        const int tm = (TMAX == 128 && rem > 64) ? 128 : (rem > 32 ? 64 : (rem > 16 ? 32 : 16));
         f(tm, g, row, min(tm, rem));
         row += tm;
       }
@@ -379,7 +382,11 @@ __device__ __forceinline__ void tile_env_advance(const AdvParams& P, unsigned ch
 
 __global__ void __launch_bounds__(NTHREADS, BM_MINBLOCKS) k_env_advance(AdvParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  for_each_tile(P.gs.goff, P.gs.ngroups, [&](int tm, int g, int row0, int nrows) {
+  for_each_tile<BM_TM128 ? 128 : 64>(P.gs.goff, P.gs.ngroups, [&](int tm, int g, int row0, int nrows) {
+#if BM_TM128
+    if (tm == 128) tile_env_advance<128>(P, smem_raw, g, row0, nrows);
+    else
+#endif
     if (tm == 64) tile_env_advance<64>(P, smem_raw, g, row0, nrows);
     else if (tm == 32) tile_env_advance<32>(P, smem_raw, g, row0, nrows);
     else tile_env_advance<16>(P, smem_raw, g, row0, nrows);
@@ -486,7 +493,11 @@ __device__ __forceinline__ void tile_psi(const PsiParams& P, unsigned char* smem
 __global__ void __launch_bounds__(NTHREADS, BM_MINBLOCKS) k_psi(PsiParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double acc_ln = 0.0, acc_zero = 0.0;       // rows finished by this thread (tid < tile height), in tile order
-  for_each_tile(P.gs.goff, P.gs.ngroups, [&](int tm, int g, int row0, int nrows) {
+  for_each_tile<BM_TM128 ? 128 : 64>(P.gs.goff, P.gs.ngroups, [&](int tm, int g, int row0, int nrows) {
+#if BM_TM128
+    if (tm == 128) tile_psi<128>(P, smem_raw, g, row0, nrows, acc_ln, acc_zero);
+    else
+#endif
     if (tm == 64) tile_psi<64>(P, smem_raw, g, row0, nrows, acc_ln, acc_zero);
     else if (tm == 32) tile_psi<32>(P, smem_raw, g, row0, nrows, acc_ln, acc_zero);
     else tile_psi<16>(P, smem_raw, g, row0, nrows, acc_ln, acc_zero);
