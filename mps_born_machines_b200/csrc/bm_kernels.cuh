@@ -41,6 +41,9 @@ constexpr int NTHREADS = 256;   // 8 warps arranged 2 (rows) x 4 (cols)
 #ifndef BM_TM128
 #define BM_TM128 0      // tuning variant: 128-row tiles in k_env_advance / k_psi (needs BM_MINBLOCKS=1, BM_STAGES=3)
 #endif
+#ifndef BM_LOAD_LATE
+#define BM_LOAD_LATE 1   // panel kernels: refill the ring after the first DMMA block of a chunk (0: right after the barrier)
+#endif
 #ifndef BM_NOEPI
 #define BM_NOEPI 0      // tuning only: skip epilogue memory traffic
 #endif
@@ -202,31 +205,28 @@ __device__ __forceinline__ void panel_gemm_all(PanelSmem<TM>& sm, const double* 
   const int nct = (Dout + TN - 1) / TN;
   const int total = nkc * nct;
 
-  // ---- per-thread staging plan, hoisted out of the chunk loop (the address arithmetic used to cost ~4 integer
-  //      instructions per DMMA): each thread owns A_IT fixed 16-byte pieces of the A tile and B_IT of the B tile.
+  // ---- per-thread staging plan.  Thread t owns the 16-byte pieces t, t + 256, ... of the A tile (row t/8 + 32 j,
+  //      doubles 2 (t%8)..) and of the B tile (k row t/64 + 4 j, doubles 2 (t%64)..): every piece after the first is a
+  //      CONSTANT shared-memory offset and a constant multiple of ldB away from the first, so one base address per
+  //      operand is all the chunk loop needs (ncu r02: the general index arithmetic cost ~170 integer instructions
+  //      and an integer division per chunk and warp, all of them between the barrier and the first DMMA).
   constexpr int A_IT = (TM * (KC / 2) + NTHREADS - 1) / NTHREADS;
   constexpr int B_IT = KC * (TN / 2) / NTHREADS;
   constexpr unsigned A_STAGE_BYTES = TM * A_STRIDE * 8, B_STAGE_BYTES = KC * B_STRIDE * 8;
+  constexpr int A_ROWS_PER_IT = NTHREADS / (KC / 2), B_ROWS_PER_IT = NTHREADS / (TN / 2);
+  const int a_r0 = tid / (KC / 2), a_c = (tid % (KC / 2)) * 2;
+  const int b_k0 = tid / (TN / 2), b_c = (tid % (TN / 2)) * 2;
+  const bool a_on = a_r0 < TM;                                       // TM = 16: only half of the threads stage A
   const double* a_src[A_IT];      // source of this thread's j-th A piece (nullptr: row outside the tile)
-  unsigned a_dst[A_IT];           // shared address in stage 0 (bit 31: piece does not exist for this tile height)
 #pragma unroll
   for (int j = 0; j < A_IT; ++j) {
-    int i = tid + j * NTHREADS;
-    int r = i / (KC / 2), c2 = i % (KC / 2);
-    bool on = i < TM * (KC / 2);
-    const double* rp = on ? rowptr[r] : nullptr;
-    a_src[j] = rp ? rp + c2 * 2 : nullptr;
-    a_dst[j] = (unsigned)__cvta_generic_to_shared(&sm.A[0][on ? r : 0][c2 * 2]) | (on ? 0u : 0x80000000u);
+    const double* rp = a_on ? rowptr[a_r0 + j * A_ROWS_PER_IT] : nullptr;
+    a_src[j] = rp ? rp + a_c : nullptr;
   }
-  unsigned b_dst[B_IT];
-  int b_off[B_IT];
-#pragma unroll
-  for (int j = 0; j < B_IT; ++j) {
-    int i = tid + j * NTHREADS;
-    int kk = i / (TN / 2), c2 = (i % (TN / 2)) * 2;
-    b_dst[j] = (unsigned)__cvta_generic_to_shared(&sm.B[0][kk][c2]);
-    b_off[j] = kk * ldB + c2;
-  }
+  const unsigned a_dst0 = (unsigned)__cvta_generic_to_shared(&sm.A[0][a_on ? a_r0 : 0][a_c]);
+  const unsigned b_dst0 = (unsigned)__cvta_generic_to_shared(&sm.B[0][b_k0][b_c]);
+  const double* const b_thr = B + (long long)b_k0 * ldB + b_c;
+  const long long b_step = (long long)B_ROWS_PER_IT * ldB;
   auto cp16 = [](unsigned dst, const void* src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
   };
@@ -235,52 +235,56 @@ __device__ __forceinline__ void panel_gemm_all(PanelSmem<TM>& sm, const double* 
   };
   bool rows_full = true;          // every piece of this thread has a valid source row (CTA-uniform when nrows == TM)
 #pragma unroll
-  for (int j = 0; j < A_IT; ++j) rows_full = rows_full && ((a_dst[j] & 0x80000000u) || a_src[j] != nullptr);
+  for (int j = 0; j < A_IT; ++j) rows_full = rows_full && (!a_on || a_src[j] != nullptr);
   rows_full = __syncthreads_and(rows_full);
 
-  auto load = [&](int it) {
-    const int stage = it % STAGES;
-    const int ct = it / nkc, kc = it - ct * nkc;
-    const int k0 = kc * KC, col0 = ct * TN;
-    if (kc == 0) pre(col0);
+  int l_kc = 0, l_ct = 0, l_stage = 0;     // chunk the NEXT load() call stages (kept incrementally: no division)
+  auto load = [&]() {
+    const int stage = l_stage;
+    const int k0 = l_kc * KC, col0 = l_ct * TN;
+    if (l_kc == 0) pre(col0);
+    if (++l_kc == nkc) { l_kc = 0; ++l_ct; }
+    l_stage = l_stage + 1 == STAGES ? 0 : l_stage + 1;
     const bool full_k = k0 + KC <= Din;
-    const double* bcol = B + (long long)k0 * ldB + col0;
+    const double* bsrc = b_thr + (long long)k0 * ldB + col0;
+    const unsigned ad = a_dst0 + stage * A_STAGE_BYTES, bd = b_dst0 + stage * B_STAGE_BYTES;
     if (BM_FASTPATH && rows_full && full_k && col0 + TN <= Dout) {      // interior chunk: no predication at all
+      if (a_on) {
 #pragma unroll
-      for (int j = 0; j < A_IT; ++j)
-        if (!(a_dst[j] & 0x80000000u)) cp16f(a_dst[j] + stage * A_STAGE_BYTES, a_src[j] + k0);
+        for (int j = 0; j < A_IT; ++j) cp16f(ad + j * (A_ROWS_PER_IT * A_STRIDE * 8), a_src[j] + k0);
+      }
 #pragma unroll
-      for (int j = 0; j < B_IT; ++j) cp16f(b_dst[j] + stage * B_STAGE_BYTES, bcol + b_off[j]);
+      for (int j = 0; j < B_IT; ++j) cp16f(bd + j * (B_ROWS_PER_IT * B_STRIDE * 8), bsrc + j * b_step);
       return;
     }
+    if (a_on) {
 #pragma unroll
-    for (int j = 0; j < A_IT; ++j) {
-      if (a_dst[j] & 0x80000000u) continue;
-      const int c2 = ((tid + j * NTHREADS) % (KC / 2)) * 2;
-      int valid = a_src[j] ? (full_k ? 2 : max(0, min(2, Din - k0 - c2))) : 0;
-      cp16(a_dst[j] + stage * A_STAGE_BYTES, valid ? (const void*)(a_src[j] + k0) : (const void*)B, valid * 8);
+      for (int j = 0; j < A_IT; ++j) {
+        int valid = a_src[j] ? (full_k ? 2 : max(0, min(2, Din - k0 - a_c))) : 0;
+        cp16(ad + j * (A_ROWS_PER_IT * A_STRIDE * 8), valid ? (const void*)(a_src[j] + k0) : (const void*)B, valid * 8);
+      }
     }
 #pragma unroll
     for (int j = 0; j < B_IT; ++j) {
-      const int i = tid + j * NTHREADS;
-      const int kk = i / (TN / 2), c2 = (i % (TN / 2)) * 2;
-      int valid = (full_k || k0 + kk < Din) ? max(0, min(2, Dout - col0 - c2)) : 0;
-      cp16(b_dst[j] + stage * B_STAGE_BYTES, valid ? (const void*)(bcol + b_off[j]) : (const void*)B, valid * 8);
+      const int kk = b_k0 + j * B_ROWS_PER_IT;
+      int valid = (full_k || k0 + kk < Din) ? max(0, min(2, Dout - col0 - b_c)) : 0;
+      cp16(bd + j * (B_ROWS_PER_IT * B_STRIDE * 8), valid ? (const void*)(bsrc + j * b_step) : (const void*)B, valid * 8);
     }
   };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < total) load(s);
+    if (s < total) load();
     cp_async_commit();
   }
-  int kc = 0, ct = 0;
+  int kc = 0, ct = 0, st = 0;
   for (int it = 0; it < total; ++it) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    if (it + STAGES - 1 < total) load(it + STAGES - 1);
+#if !BM_LOAD_LATE
+    if (it + STAGES - 1 < total) load();
     cp_async_commit();
-    const int st = it % STAGES;
+#endif
 #pragma unroll
     for (int ks = 0; ks < KC; ks += 4) {
       double a[MT], b[4];
@@ -292,7 +296,16 @@ __device__ __forceinline__ void panel_gemm_all(PanelSmem<TM>& sm, const double* 
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+#if BM_LOAD_LATE
+      // the stage freed by the barrier above is refilled AFTER the first quarter of the chunk's DMMAs are queued:
+      // the staging instructions of the warps then overlap the pipe instead of sitting between the barrier and it
+      if (ks == 0) {
+        if (it + STAGES - 1 < total) load();
+        cp_async_commit();
+      }
+#endif
     }
+    st = st + 1 == STAGES ? 0 : st + 1;
     if (++kc == nkc) {
       epi(ct * TN, acc);
 #pragma unroll
@@ -567,23 +580,54 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int nkc = (cnt + KC - 1) / KC;
+  // staging plan: thread t owns the pieces t and t + 512 of either operand (sample row t/64 + 8 j of the chunk, doubles
+  // 2 (t%64)..): constant shared-memory offsets from one base; interior chunks of interior tiles carry no predication
+  constexpr int G_IT = KC * (GT / 2) / GRAD_THREADS, G_ROWS_PER_IT = GRAD_THREADS / (GT / 2);
+  const int l_kk = tid / (GT / 2), l_c = (tid % (GT / 2)) * 2;
+  const unsigned l_dst0 = (unsigned)__cvta_generic_to_shared(&sm.Ls[0][l_kk][l_c]);
+  const unsigned r_dst0 = (unsigned)__cvta_generic_to_shared(&sm.Rs[0][l_kk][l_c]);
+  const unsigned w_dst0 = (unsigned)__cvta_generic_to_shared(&sm.w[0][tid < KC ? tid : 0]);
+  constexpr unsigned G_STAGE_BYTES = sizeof(sm.Ls[0]), W_STAGE_BYTES = sizeof(sm.w[0]);
+  static_assert(sizeof(sm.Ls[0]) == sizeof(sm.Rs[0]), "operand stages differ");
+  const double* const l_thr = P.Lenv + a0 + l_c;
+  const double* const r_thr = P.Renv + c0 + l_c;
+  const bool interior = a0 + GT <= P.Dl && c0 + GT <= P.Dr;
+  auto cp16f = [](unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+  };
+  auto cp16 = [](unsigned dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+  };
+  auto cp8 = [](unsigned dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+  };
   auto load = [&](int stage, int kc) {
     const int k0 = kc * KC;
-    for (int i = tid; i < KC * (GT / 2); i += GRAD_THREADS) {
-      int kk = i / (GT / 2), c2 = i % (GT / 2);
-      int k = k0 + kk;
-      bool rv = k < cnt;
-      long long id = rv ? sm.idx[k] : 0;
-      int ca = a0 + c2 * 2, cc = c0 + c2 * 2;
-      int va = rv ? max(0, min(2, P.Dl - ca)) : 0;
-      int vc = rv ? max(0, min(2, P.Dr - cc)) : 0;
-      cp_async16(&sm.Ls[stage][kk][c2 * 2], va ? (const void*)(P.Lenv + id * P.ldL + ca) : (const void*)P.Lenv, va * 8);
-      cp_async16(&sm.Rs[stage][kk][c2 * 2], vc ? (const void*)(P.Renv + id * P.ldR + cc) : (const void*)P.Renv, vc * 8);
+    const unsigned ld = l_dst0 + stage * G_STAGE_BYTES, rd = r_dst0 + stage * G_STAGE_BYTES;
+    if (BM_FASTPATH && interior && k0 + KC <= cnt) {
+#pragma unroll
+      for (int j = 0; j < G_IT; ++j) {
+        const long long id = sm.idx[k0 + l_kk + j * G_ROWS_PER_IT];
+        cp16f(ld + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Ls[0][0])), l_thr + id * P.ldL);
+        cp16f(rd + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Rs[0][0])), r_thr + id * P.ldR);
+      }
+      if (tid < KC) cp8(w_dst0 + stage * W_STAGE_BYTES, P.winv + sm.idx[k0 + tid], 8);
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < G_IT; ++j) {
+      const int k = k0 + l_kk + j * G_ROWS_PER_IT;
+      const bool rv = k < cnt;
+      const long long id = rv ? sm.idx[k] : 0;
+      const int va = rv ? max(0, min(2, P.Dl - a0 - l_c)) : 0;
+      const int vc = rv ? max(0, min(2, P.Dr - c0 - l_c)) : 0;
+      cp16(ld + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Ls[0][0])), va ? (const void*)(l_thr + id * P.ldL) : (const void*)P.Lenv, va * 8);
+      cp16(rd + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Rs[0][0])), vc ? (const void*)(r_thr + id * P.ldR) : (const void*)P.Renv, vc * 8);
     }
     if (tid < KC) {
-      int k = k0 + tid;
-      bool rv = k < cnt;
-      cp_async8(&sm.w[stage][tid], rv ? (const void*)(P.winv + sm.idx[k]) : (const void*)P.winv, rv ? 8 : 0);
+      const int k = k0 + tid;
+      const bool rv = k < cnt;
+      cp8(w_dst0 + stage * W_STAGE_BYTES, rv ? (const void*)(P.winv + sm.idx[k]) : (const void*)P.winv, rv ? 8 : 0);
     }
   };
 #pragma unroll
@@ -591,13 +635,14 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
     if (s < nkc) load(s, s);
     cp_async_commit();
   }
+  int st = 0, nst = GSTAGES - 1;
   for (int kc = 0; kc < nkc; ++kc) {
     cp_async_wait<GSTAGES - 2>();
     __syncthreads();
-    int nx = kc + GSTAGES - 1;
-    if (nx < nkc) load(nx % GSTAGES, nx);
+#if !BM_LOAD_LATE
+    if (kc + GSTAGES - 1 < nkc) load(nst, kc + GSTAGES - 1);
     cp_async_commit();
-    const int st = kc % GSTAGES;
+#endif
 #pragma unroll
     for (int ks = 0; ks < KC; ks += 4) {
       double a[4], b[4];
@@ -610,7 +655,15 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+#if BM_LOAD_LATE
+      if (ks == 0) {      // refill the freed stage once the first DMMA block is queued (see panel_gemm_all)
+        if (kc + GSTAGES - 1 < nkc) load(nst, kc + GSTAGES - 1);
+        cp_async_commit();
+      }
+#endif
     }
+    st = st + 1 == GSTAGES ? 0 : st + 1;
+    nst = nst + 1 == GSTAGES ? 0 : nst + 1;
   }
   cp_async_wait<0>();
 
