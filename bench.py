@@ -14,6 +14,7 @@ Workload "c3" (default): synthetic binarised 28x28, 60 000 samples in total (sha
 strong scaling), L=784, D=256 everywhere (random right/left-canonical MPS, centre at the first timed bond).
 """
 import argparse
+import gc
 import json
 import math
 import os
@@ -295,6 +296,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
         except Exception as exc:          # e.g. CUDA IPC unavailable in this container: fall back to NCCL, say so
             allreduce_mode = f'nccl (peer-memory path unavailable: {exc})'
     trace('setup done')
+    gc.collect(); gc.freeze()      # a full collection over torch's object graph costs tens of ms: not inside a timed loop
     eng.env_build(start)
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
@@ -380,20 +382,29 @@ def measure_steps(args, workload, rank, world, local, full=True):
     cache = T.ImgCache(eng, shard)
     site_bytes = lambda j: int(fmps.tensors[j].data.nbytes)
     h2d = d2h = 0
+    for i in range(min(args.warmup, 3)):   # warm-up of the facade path itself (staging buffers, first foreign uploads)
+        tn = T.learning_step_cached(fmps, k, None, lr, cache, True, **kw)
+        T._write_back(fmps, k, tn)
+        T.sequential_update(fmps, None, cache, k, True)
+        k += 1
     eng._h2d_bytes = 0
     barrier()
     e0 = time.perf_counter()
+    wall = []
     for i in range(steps):
+        w0 = time.perf_counter()
         tn = T.learning_step_cached(fmps, k, None, lr, cache, True, **kw)
         T._write_back(fmps, k, tn)
         T.sequential_update(fmps, None, cache, k, True)
         d2h += site_bytes(k) + site_bytes(k + 1) + 64
         k += 1
+        wall.append(round((time.perf_counter() - w0) * 1e3, 3))
     barrier()
     h2d = eng._h2d_bytes                  # bytes the facade actually uploaded (tensors it handed out itself are not re-sent)
     e2e_value = N * steps / max_over_ranks(time.perf_counter() - e0)
     e2e = {'value': e2e_value, 'unit': 'sample·site updates/s', 'h2d_bytes_per_step': h2d // steps, 'd2h_bytes_per_step': d2h // steps,
-           'api': 'facade TNutils.learning_step_cached + write-back + sequential_update, host numpy tensors in and out'}
+           'api': 'facade TNutils.learning_step_cached + write-back + sequential_update, host numpy tensors in and out',
+           'host_wall_ms_per_step': wall}
 
     trace('facade e2e done')
     # ---- e2e (b): the engine-level call with PINNED host site tensors (BornEngine.learning_step_host)

@@ -118,10 +118,14 @@ int bm_step_update(bm_ctx* ctx, int k, const double* S_dev, double batch_total, 
                    double* scalars_host, double* s_host);
 
 /* One whole two-site step in one call: learning_step_cached + write-back + sequential_update
- * (TNutils.py:1603-1620) = bm_step_grad + bm_step_update (+ bm_env_advance when advance != 0) without
- * returning to the caller in between; the host synchronises once per Gram level (eigenvalues) and once at
- * the end.  S_dev: scratch of rows*ld + 2 doubles (bm_grad_dims).  With several ranks this entry needs the
- * fused peer all-reduce (bm_peer_import); the NCCL path goes through bm_step_grad / bm_step_update. */
+ * (TNutils.py:1603-1620) = bm_step_grad + bm_step_update (+ bm_env_advance when advance & 1) without
+ * returning to the caller in between; the host synchronises once per Gram level (eigenvalues) and once when the
+ * new site tensors and the scalars are complete -- the call returns while the environment advance is still running
+ * on the context's stream (everything later is ordered behind it).  advance & 2: additionally leave the two new site
+ * tensors in the reference layout on the device, so that the next bm_get_site of sites k, k+1 is a plain copy that
+ * overlaps the advance (the per-step download of learning_step_cached).  S_dev: scratch of rows*ld + 2 doubles
+ * (bm_grad_dims).  With several ranks this entry needs the fused peer all-reduce (bm_peer_import); the NCCL path goes
+ * through bm_step_grad / bm_step_update. */
 int bm_step(bm_ctx* ctx, int k, const int32_t* mask_host, int n_mask, double* S_dev, double batch_total,
             double lr, int renorm, int going_right, int max_bond, double cutoff, double mom_bias, int advance,
             double* scalars_host, double* s_host);

@@ -422,14 +422,21 @@ def _upload_site(eng, site, data):
     if not _same_as_engine(eng, site, data):
         eng.set_site(site, data)
         getattr(eng, '_handed_out', {}).pop(site, None)
+        eng._advanced = None
         eng._h2d_bytes = getattr(eng, '_h2d_bytes', 0) + int(np.asarray(data).nbytes)
 
 
 def sequential_update(mps, _imgs, img_cache, site, going_right):
-    """TNutils.py:504-526: refresh the cache for ALL images after the two tensors at (site, site+1) changed."""
+    """TNutils.py:504-526: refresh the cache for ALL images after the two tensors at (site, site+1) changed.
+    `learning_step_cached` already enqueued this advance behind its split (it runs while the new tensors are being
+    downloaded); when the MPS still holds exactly the tensors that step returned there is nothing left to do."""
     eng = img_cache.engine
     _upload_site(eng, site, mps.tensors[site].data)            # skipped when the tensors are the ones the step just returned
     _upload_site(eng, site + 1, mps.tensors[site + 1].data)
+    if getattr(eng, '_advanced', None) == (site, bool(going_right)):
+        eng._advanced = None
+        return
+    eng._advanced = None
     eng.env_build(site)
     eng.env_advance(site, going_right)
 
@@ -498,7 +505,11 @@ def learning_step_cached(mps, index, _imgs, lr, img_cache, going_right=True,
         out = eng.step_with_update_fn(index, _lr_value(lr), lambda site, dn: _as_array(update_wrap(site, _dnll_tensor(site, dn, len(mps.tensors)))).reshape(dn.shape),
                                       going_right, renorm, max_bond, cutoff, mask, advance=False)
     else:
-        out = eng.step(index, _lr_value(lr), going_right, renorm, max_bond, cutoff, mask, mom_bias, advance=False)
+        # advance=True: the `sequential_update` that follows every step in the reference's loop (TNutils.py:1620) is
+        # enqueued right behind the split and overlaps the download of the two new tensors
+        out = eng.step(index, _lr_value(lr), going_right, renorm, max_bond, cutoff, mask, mom_bias, advance=True,
+                       stage_sites=True)
+        eng._advanced = (index, bool(going_right))
     if isinstance(owner, mps_lr) and not out['skipped']:
         owner.past_grad[index] = out['mean_dnll']
     if out['skipped']:

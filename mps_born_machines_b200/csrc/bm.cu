@@ -117,6 +117,12 @@ struct bm_ctx {
   cudaEvent_t ev_sync = nullptr;   // host waits (spinning) on this event instead of a blocking stream synchronise
   cudaStream_t side = nullptr;     // side stream: the compact-WY factors are built while the eigenvalues are being bisected
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_sites = nullptr;  // recorded on `stream` after the last launch that wrote a site tensor (bm_get_site reads on `side`)
+  cudaEvent_t ev_up = nullptr, ev_stage_free = nullptr;   // bm_set_site: upload on `side`, conversion on `stream`
+  double* stage_out = nullptr; size_t stage_out_cap = 0;  // device staging of bm_get_site (side stream)
+  double* stage_up = nullptr; size_t stage_up_cap = 0;    // device staging of bm_set_site (side stream)
+  double* stage_pair[2] = {nullptr, nullptr};             // bm_step(advance & 2): the two new sites in the reference layout
+  int staged_k[2] = {-1, -1};                              //   which sites they hold (-1: nothing)
   double* h_scal = nullptr; int* h_iscal = nullptr;   // pinned
   double* stage = nullptr; size_t stage_cap = 0;      // device staging for host<->device tensor moves
   int last_k = -1; int last_B = 0; const int* last_ids = nullptr;
@@ -404,12 +410,15 @@ void dbg_flush(bm_ctx* c) {
 
 // Host waits for everything enqueued so far by spinning on an event (a blocking cudaStreamSynchronize costs tens of
 // microseconds of wake-up latency, twice per two-site step).
-int wait_stream(bm_ctx* c) {
-  CU(cudaEventRecord(c->ev_sync, c->stream));
+int poll_sync(bm_ctx* c) {                                  // spin until the last cudaEventRecord(ev_sync) has completed
   cudaError_t e;
   while ((e = cudaEventQuery(c->ev_sync)) == cudaErrorNotReady) {}
   if (e != cudaSuccess) return fail(c, BM_ECUDA, std::string("device error: ") + cudaGetErrorString(e));
   return BM_OK;
+}
+int wait_stream(bm_ctx* c) {
+  CU(cudaEventRecord(c->ev_sync, c->stream));
+  return poll_sync(c);
 }
 #define WAIT()                                             \
   do {                                                     \
@@ -705,6 +714,9 @@ int bm_create(bm_ctx** out, int device, int n_sites, int phys_dim, int max_bond_
     CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_sites, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming));
   }
   CU(cudaMallocHost((void**)&c->h_scal, 16 * sizeof(double)));
   CU(cudaMallocHost((void**)&c->h_iscal, 4 * sizeof(int)));
@@ -716,12 +728,13 @@ int bm_destroy(bm_ctx* c) {
   if (!c) return BM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->side) cudaStreamSynchronize(c->side);
   for (int r = 0; r < PEER_MAX; ++r) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
   if (c->peer_buf) cudaFree(c->peer_buf);
   if (c->tail_local) cudaFree(c->tail_local);
   void* ptrs[] = {c->Lform, c->Rform, c->phys, c->perm, c->goff, c->bperm, c->bgoff, c->bmask, c->E, c->emax, c->cume,
                   c->tfL, c->tfR, c->rbEst, c->rbEc[0], c->rbEc[1], c->rbT, c->rbV[0], c->rbV[1], c->rbU, c->rbPix, c->rbSel, c->tf_status, c->Aint, c->A2, c->W, c->Ssv, c->U, c->V, c->G, c->sgn, c->Gq, c->Yb[0], c->Yb[1], c->Tb[0], c->Tb[1], c->Tmp, c->lam, c->eD, c->eE, c->eTau, c->eV, c->eZ, c->eZn, c->eC, c->eU2, c->eDev, c->eLam, c->eGm, c->eT, c->eProf, c->eBt, c->eRn, c->eig_status, c->work, c->info, c->iscal, c->psi, c->winv, c->lnpsi,
-                  c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
+                  c->ws, c->partZ, c->part2, c->psi_part, c->scal, c->stage, c->stage_out, c->stage_up, c->stage_pair[0], c->stage_pair[1], c->chain.V[0], c->chain.V[1], c->chain.e[0], c->chain.e[1],
                   c->chain.cume[0], c->chain.cume[1], c->chain.norm[0], c->chain.norm[1], c->chain.phys, c->chain.perm,
                   c->chain.goff, c->chain.goff_all, c->chain.rej_list, c->chain.rej_count, c->chain.U, c->chain.lnabs, c->chain.sign};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -736,6 +749,9 @@ int bm_destroy(bm_ctx* c) {
   if (c->ev_sync) cudaEventDestroy(c->ev_sync);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_sites) cudaEventDestroy(c->ev_sites);
+  if (c->ev_up) cudaEventDestroy(c->ev_up);
+  if (c->ev_stage_free) cudaEventDestroy(c->ev_stage_free);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->gesvdj) cusolverDnDestroyGesvdjInfo(c->gesvdj);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
@@ -935,13 +951,24 @@ int bm_set_site(bm_ctx* c, int k, const double* lrp_host, int Dl, int Dr) {
   REQUIRE((k != 0 || Dl == 1) && (k != c->L - 1 || Dr == 1), "bm_set_site: boundary sites need an outer bond of 1");
   CU(cudaSetDevice(c->device));
   size_t cnt = (size_t)Dl * Dr * c->d;
-  int r = ensure_stage(c, cnt);
-  if (r != BM_OK) return r;
-  CU(cudaMemcpyAsync(c->stage, lrp_host, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  k_site_from_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(c->stage, c->d, Dl, Dr, c->Lf(k), c->Rf(k));
+  // The upload runs on the side stream, so that it overlaps whatever the main stream is still doing (bm_step returns
+  // while the environment advance of the step is running); only the layout conversion is ordered behind it.
+  if (cnt > c->stage_up_cap) {
+    CU(cudaStreamSynchronize(c->stream));                // the previous conversion may still read the old buffer
+    DALLOC(c->stage_up, cnt);
+    c->stage_up_cap = cnt;
+  }
+  for (int i = 0; i < 2; ++i) if (c->staged_k[i] == k) c->staged_k[i] = -1;
+  CU(cudaStreamWaitEvent(c->side, c->ev_stage_free, 0));  // previous conversion out of the staging buffer
+  CU(cudaMemcpyAsync(c->stage_up, lrp_host, cnt * sizeof(double), cudaMemcpyHostToDevice, c->side));
+  CU(cudaEventRecord(c->ev_up, c->side));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+  k_site_from_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(c->stage_up, c->d, Dl, Dr, c->Lf(k), c->Rf(k));
   c->launches++;
   KCHECK();
-  CU(cudaStreamSynchronize(c->stream));   // lrp_host may be pageable and freed by the caller
+  CU(cudaEventRecord(c->ev_stage_free, c->stream));
+  CU(cudaEventRecord(c->ev_sites, c->stream));
+  CU(cudaStreamSynchronize(c->side));     // lrp_host may be pageable and freed by the caller
   c->sDl[k] = Dl; c->sDr[k] = Dr;
   invalidate_site(c, k);
   return BM_OK;
@@ -961,13 +988,28 @@ int bm_get_site(bm_ctx* c, int k, double* lrp_host, int* Dl, int* Dr) {
   REQUIRE(c->sDl[k] > 0, "bm_get_site: site not set");
   CU(cudaSetDevice(c->device));
   size_t cnt = (size_t)c->sDl[k] * c->sDr[k] * c->d;
-  int r = ensure_stage(c, cnt);
-  if (r != BM_OK) return r;
-  k_site_to_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(c->Lf(k), c->d, c->sDl[k], c->sDr[k], c->stage);
+  // Conversion and download run on the side stream behind the last launch that WROTE a site tensor: a download right
+  // after bm_step overlaps the environment advance, which only reads the sites.
+  for (int i = 0; i < 2; ++i)
+    if (c->staged_k[i] == k) {          // bm_step left this site in the reference layout: copy engine only, no kernel
+      CU(cudaStreamWaitEvent(c->side, c->ev_sites, 0));
+      CU(cudaMemcpyAsync(lrp_host, c->stage_pair[i], cnt * sizeof(double), cudaMemcpyDeviceToHost, c->side));
+      CU(cudaStreamSynchronize(c->side));
+      if (Dl) *Dl = c->sDl[k];
+      if (Dr) *Dr = c->sDr[k];
+      return BM_OK;
+    }
+  if (cnt > c->stage_out_cap) {
+    CU(cudaStreamSynchronize(c->side));
+    DALLOC(c->stage_out, cnt);
+    c->stage_out_cap = cnt;
+  }
+  CU(cudaStreamWaitEvent(c->side, c->ev_sites, 0));
+  k_site_to_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->side>>>(c->Lf(k), c->d, c->sDl[k], c->sDr[k], c->stage_out);
   c->launches++;
   KCHECK();
-  CU(cudaMemcpyAsync(lrp_host, c->stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(lrp_host, c->stage_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->side));
+  CU(cudaStreamSynchronize(c->side));
   if (Dl) *Dl = c->sDl[k];
   if (Dr) *Dr = c->sDr[k];
   return BM_OK;
@@ -1099,12 +1141,12 @@ int bm_step_grad(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double*
   {
     const bool tf32 = c->grad_tf32 && Dl <= TF_TILE && Dr <= TF_TILE;
     const bool tma = tf32 && c->grad_tf32 == 2 && G <= TM_MAXG;
-    const int kstep = tma ? 32 : KC;              // a TMA box holds 32 samples: splits must not cut one
+    const int kstep = tma ? 32 : (tf32 ? KC : GKC);   // a TMA box holds 32 samples: splits must not cut one; FP64: whole chunks
     const int tiles_a = tf32 ? 1 : (Dl + GT - 1) / GT, tiles_c = tf32 ? 1 : (Dr + GT - 1) / GT;
     int maxg = 0;
     for (int g = 0; g < G; ++g) maxg = std::max(maxg, h_goff[g + 1] - h_goff[g]);
-    // samples per split: minimise the makespan  ceil(items / #SM) * kchunk  over multiples of 16
-    int kchunk = KC, nsplit = 0;
+    // samples per split: minimise the makespan  ceil(items / #SM) * kchunk  over multiples of the chunk
+    int kchunk = kstep, nsplit = 0;
     {
       double best = 1e300;
       for (int kc = kstep; kc <= GRAD_MAXCHUNK; kc += kstep) {
@@ -1453,6 +1495,19 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail
                                                  c->Lf(k), c->Rf(k), c->Lf(k + 1), c->Rf(k + 1));
     c->launches += 2;
     KCHECK();
+    c->staged_k[0] = c->staged_k[1] = -1;
+    if ((advance & 2) && gram) {      // chi is known on the host: leave both new sites in the reference layout for bm_get_site
+      for (int i = 0; i < 2; ++i) {
+        const int sdl = i == 0 ? Dl : chi, sdr = i == 0 ? chi : Dr;
+        const size_t cnt = (size_t)sdl * sdr * d;
+        if (!c->stage_pair[i]) DALLOC(c->stage_pair[i], (size_t)c->Dcap * c->Dcap * d);
+        k_site_to_ref<<<(int)std::min<size_t>((cnt + 255) / 256, 1024), 256, 0, c->stream>>>(c->Lf(k + i), d, sdl, sdr, c->stage_pair[i]);
+        c->staged_k[i] = k + i;
+      }
+      c->launches += 2;
+      KCHECK();
+    }
+    CU(cudaEventRecord(c->ev_sites, c->stream));
     return BM_OK;
   };
   auto set_dims = [&](int x) {
@@ -1460,14 +1515,14 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail
     invalidate_site(c, k); invalidate_site(c, k + 1);
   };
   auto do_advance = [&]() -> int {                              // sequential_update on the new isometric site
-    if (!advance) return BM_OK;
+    if (!(advance & 1)) return BM_OK;
     if (going_right) { c->vl = k; return adv_right(c, k); }
     c->vr = k + 2;
     return adv_left(c, k + 1);
   };
   // environments the advance needs must be valid BEFORE the sites change (invalidate_site resets the bookkeeping)
   const int vl0 = c->vl, vr0 = c->vr;
-  if (advance) {
+  if (advance & 1) {
     if (going_right) REQUIRE(vl0 >= k, "bm_step: left environment of bond k is not valid");
     else REQUIRE(vr0 <= k + 2, "bm_step: right environment of bond k+2 is not valid");
   }
@@ -1491,13 +1546,23 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail
   int r = write_back();
   if (r != BM_OK) return r;
   dbg_tick(c, "writeback");
-  if (gram) {                       // chi is known on the host: the environment advance can be enqueued before the final wait
+  if (gram) {
+    // chi is known on the host: the environment advance is enqueued BEHIND the event the host waits for, so the call
+    // returns (and the caller prepares its next step, downloads the new tensors, ...) while the advance is running
+    CU(cudaEventRecord(c->ev_sync, c->stream));
     set_dims(chi);
     r = do_advance();
     if (r != BM_OK) return r;
+    dbg_tick(c, "advance]");
+    if (c->eig_debug) WAIT();       // the debug ticks are read below
+    else {
+      r = poll_sync(c);
+      if (r != BM_OK) return r;
+    }
+  } else {
+    dbg_tick(c, "advance]");
+    WAIT();
   }
-  dbg_tick(c, "advance]");
-  WAIT();
   dbg_flush(c);
   if (gram && fast) {
     if (gram_fast_verified(c)) c->eig_fast++;
@@ -1575,7 +1640,7 @@ int bm_step(bm_ctx* c, int k, const int32_t* mask_host, int n_mask, double* S_de
   if (r != BM_OK) return r;
   const int d = c->d, Dl = c->sDl[k], Dr = c->sDr[k + 1];
   const double* tail = S_dev + (size_t)d * Dl * d * even(Dr);
-  return update_tail(c, k, S_dev, tail, batch_total, lr, renorm, going_right, clamp_bond(c, max_bond), cutoff, mom_bias, advance ? 1 : 0,
+  return update_tail(c, k, S_dev, tail, batch_total, lr, renorm, going_right, clamp_bond(c, max_bond), cutoff, mom_bias, advance & 3,
                      scalars_host, s_host);
 }
 

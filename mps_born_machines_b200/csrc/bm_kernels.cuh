@@ -50,6 +50,10 @@ constexpr int NTHREADS = 256;   // 8 warps arranged 2 (rows) x 4 (cols)
 constexpr int STAGES = BM_STAGES;       // panel kernels: 4 x 27 KB = 106 KB -> still 2 CTAs / SM
 constexpr int UNIT = BM_UNIT;           // rows per scheduling unit (16, 32 or 64)
 constexpr int GSTAGES = 3;      // gradient kernel ring
+#ifndef BM_GKC
+#define BM_GKC 32
+#endif
+constexpr int GKC = BM_GKC;     // samples per stage of the gradient kernel (3 x 2 x 33 KB at 32: one CTA per SM anyway)
 constexpr int A_STRIDE = KC + 4;   // 20: row stride (doubles) == 4 mod 16 -> conflict-free 8x4 fragment reads
 constexpr int B_STRIDE = TN + 4;   // 132
 constexpr double LN2 = 0.69314718055994530942;
@@ -538,9 +542,9 @@ constexpr int G_STRIDE = GT + 4;     // 132
 constexpr int GRAD_MAXCHUNK = 2048;  // samples per CTA (indices cached in shared memory)
 
 struct GradSmem {
-  double Ls[GSTAGES][KC][G_STRIDE];
-  double Rs[GSTAGES][KC][G_STRIDE];
-  double w[GSTAGES][KC];
+  double Ls[GSTAGES][GKC][G_STRIDE];
+  double Rs[GSTAGES][GKC][G_STRIDE];
+  double w[GSTAGES][GKC];
   int idx[GRAD_MAXCHUNK];
 };
 
@@ -549,7 +553,7 @@ struct GradParams {
   const double* Renv; int ldR; int Dr;
   const double* winv;
   const int* perm; const int* goff; int ngroups; int d;
-  int kchunk;                      // samples per split, multiple of KC, <= GRAD_MAXCHUNK
+  int kchunk;                      // samples per split, <= GRAD_MAXCHUNK
   double* ws; long long ws_stride; // partial slot stride in doubles
   int ldA; int ldRpad;
   int tiles_c;                     // number of column tiles
@@ -579,14 +583,14 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int nkc = (cnt + KC - 1) / KC;
+  const int nkc = (cnt + GKC - 1) / GKC;
   // staging plan: thread t owns the pieces t and t + 512 of either operand (sample row t/64 + 8 j of the chunk, doubles
   // 2 (t%64)..): constant shared-memory offsets from one base; interior chunks of interior tiles carry no predication
-  constexpr int G_IT = KC * (GT / 2) / GRAD_THREADS, G_ROWS_PER_IT = GRAD_THREADS / (GT / 2);
+  constexpr int G_IT = GKC * (GT / 2) / GRAD_THREADS, G_ROWS_PER_IT = GRAD_THREADS / (GT / 2);
   const int l_kk = tid / (GT / 2), l_c = (tid % (GT / 2)) * 2;
   const unsigned l_dst0 = (unsigned)__cvta_generic_to_shared(&sm.Ls[0][l_kk][l_c]);
   const unsigned r_dst0 = (unsigned)__cvta_generic_to_shared(&sm.Rs[0][l_kk][l_c]);
-  const unsigned w_dst0 = (unsigned)__cvta_generic_to_shared(&sm.w[0][tid < KC ? tid : 0]);
+  const unsigned w_dst0 = (unsigned)__cvta_generic_to_shared(&sm.w[0][tid < GKC ? tid : 0]);
   constexpr unsigned G_STAGE_BYTES = sizeof(sm.Ls[0]), W_STAGE_BYTES = sizeof(sm.w[0]);
   static_assert(sizeof(sm.Ls[0]) == sizeof(sm.Rs[0]), "operand stages differ");
   const double* const l_thr = P.Lenv + a0 + l_c;
@@ -602,16 +606,16 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
   };
   auto load = [&](int stage, int kc) {
-    const int k0 = kc * KC;
+    const int k0 = kc * GKC;
     const unsigned ld = l_dst0 + stage * G_STAGE_BYTES, rd = r_dst0 + stage * G_STAGE_BYTES;
-    if (BM_FASTPATH && interior && k0 + KC <= cnt) {
+    if (BM_FASTPATH && interior && k0 + GKC <= cnt) {
 #pragma unroll
       for (int j = 0; j < G_IT; ++j) {
         const long long id = sm.idx[k0 + l_kk + j * G_ROWS_PER_IT];
         cp16f(ld + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Ls[0][0])), l_thr + id * P.ldL);
         cp16f(rd + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Rs[0][0])), r_thr + id * P.ldR);
       }
-      if (tid < KC) cp8(w_dst0 + stage * W_STAGE_BYTES, P.winv + sm.idx[k0 + tid], 8);
+      if (tid < GKC) cp8(w_dst0 + stage * W_STAGE_BYTES, P.winv + sm.idx[k0 + tid], 8);
       return;
     }
 #pragma unroll
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
       cp16(ld + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Ls[0][0])), va ? (const void*)(l_thr + id * P.ldL) : (const void*)P.Lenv, va * 8);
       cp16(rd + j * (G_ROWS_PER_IT * (unsigned)sizeof(sm.Rs[0][0])), vc ? (const void*)(r_thr + id * P.ldR) : (const void*)P.Renv, vc * 8);
     }
-    if (tid < KC) {
+    if (tid < GKC) {
       const int k = k0 + tid;
       const bool rv = k < cnt;
       cp8(w_dst0 + stage * W_STAGE_BYTES, rv ? (const void*)(P.winv + sm.idx[k]) : (const void*)P.winv, rv ? 8 : 0);
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) k_grad(GradParams P) {
     cp_async_commit();
 #endif
 #pragma unroll
-    for (int ks = 0; ks < KC; ks += 4) {
+    for (int ks = 0; ks < GKC; ks += 4) {
       double a[4], b[4];
       const double wv = sm.w[st][ks + (lane & 3)];
 #pragma unroll

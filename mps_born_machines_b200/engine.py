@@ -29,6 +29,8 @@ def sweep_schedule(L):
 
 
 class BornEngine:
+    _advanced = None      # (bond, going_right) of the last step whose environment advance is already enqueued (facade)
+
     def __init__(self, n_sites, max_bond, phys_dim=2, device=None, svd='gram', dist_group=None, precision='fp64',
                  standalone=False):
         if not torch.cuda.is_available():
@@ -129,13 +131,15 @@ class BornEngine:
             raise ValueError(f'n_total={n_total} does not match the sum of the shard sizes {self.shard_sizes}')
 
     def set_site(self, k, t):
+        self._advanced = None
         t = np.asarray(t, dtype=np.float64)
         if t.ndim == 2:
             t = t.reshape(1, t.shape[0], t.shape[1]) if k == 0 else t.reshape(t.shape[0], 1, t.shape[1])
         t = np.ascontiguousarray(t)
         if t.shape[2] != self.d:
             raise ValueError('physical dimension mismatch')
-        if not np.isfinite(t).all():
+        # NaN and inf always survive a sum; only a non-finite sum pays for the exact elementwise test
+        if not math.isfinite(float(t.sum())) and not np.isfinite(t).all():
             raise ValueError(f'site tensor {k} holds non-finite entries')
         check(self._ctx, self._lib.bm_set_site(self._ctx, k, _ptr(t), t.shape[0], t.shape[1]))
 
@@ -201,6 +205,7 @@ class BornEngine:
 
     def step_update(self, k, S, batch_total, lr, going_right=True, renorm='max', max_bond=None, cutoff=1e-10,
                     mom_bias=0.0, want_s=False):
+        self._advanced = None
         rows, ld, Dl, Dr, _ = self.grad_dims(k)
         scal = np.zeros(8)
         s = np.empty(min(rows, self.d * Dr)) if want_s else None
@@ -224,10 +229,13 @@ class BornEngine:
         return out
 
     def step(self, k, lr, going_right=True, renorm='max', max_bond=None, cutoff=1e-10, mask=None, mom_bias=0.0,
-             want_s=False, batch_total=None, advance=True):
+             want_s=False, batch_total=None, advance=True, stage_sites=False):
         """One learning_step_cached + write-back + sequential_update (TNutils.py:1603-1620).  Single GPU and the
         fused peer all-reduce run the whole step inside ONE library call (bm_step); the NCCL path needs the collective
-        between the gradient and the update and goes through step_grad / step_update."""
+        between the gradient and the update and goes through step_grad / step_update.  The call returns while the
+        environment advance is still running on the stream; `stage_sites` leaves the two new tensors ready for
+        `get_site` (a plain copy that overlaps the advance)."""
+        self._advanced = None
         if batch_total is None:
             if mask is not None and self.world > 1:
                 raise ValueError('multi-rank minibatch steps need batch_total (the global number of samples used by '
@@ -249,7 +257,8 @@ class BornEngine:
             code = self._lib.bm_step(self._ctx, k, _ptr(m) if m is not None else None, m.size if m is not None else 0,
                                      C.c_void_p(self._S.data_ptr()), float(batch_total), float(lr), RENORM[renorm],
                                      1 if going_right else 0, int(max_bond) if max_bond else 0, float(cutoff),
-                                     float(mom_bias), 1 if advance else 0, _ptr(scal), _ptr(s) if want_s else None)
+                                     float(mom_bias), (1 if advance else 0) | (2 if stage_sites else 0), _ptr(scal),
+                                     _ptr(s) if want_s else None)
             check(self._ctx, code)
             out = self._step_result(scal, s, want_s)
         out['nll_batch'] = -2.0 * out['sum_logpsi'] / batch_total + math.log(out['Z']) if out['Z'] > 0 else float('nan')
@@ -257,6 +266,7 @@ class BornEngine:
 
     def split_bond(self, k, going_right=False, max_bond=None, cutoff=1e-10, want_s=False):
         """merge + truncated split of bond k, no gradient step (compress, TNutils.py:930-947)."""
+        self._advanced = None
         rows, ld, Dl, Dr, _ = self.grad_dims(k)
         scal = np.zeros(8)
         s = np.empty(min(rows, self.d * Dr)) if want_s else None
@@ -282,7 +292,7 @@ class BornEngine:
         device-resident environments, downloads the two new site tensors."""
         self.set_site(k, site_k)
         self.set_site(k + 1, site_k1)
-        out = self.step(k, lr, going_right, **kw)
+        out = self.step(k, lr, going_right, stage_sites=True, **kw)
         return self.get_site(k), self.get_site(k + 1), out
 
     def step_with_update_fn(self, k, lr, fn, going_right=True, renorm='max', max_bond=None, cutoff=1e-10, mask=None,
@@ -290,6 +300,7 @@ class BornEngine:
         """Two-site step with an arbitrary host-side `update_wrap(site, dNLL) -> update` (TNutils.py:1541).
         dNLL = A/Z - S/B is formed on the host from the device results, `fn` is applied, and an equivalent
         S' = B (A/Z - update) is uploaded so that the device update A - lr*(A/Z - S'/B) equals A - lr*update."""
+        self._advanced = None
         S = self.step_grad(k, mask)
         if self.world > 1 and not self.peer:
             allreduce_sum_(S, self.group)
@@ -330,6 +341,7 @@ class BornEngine:
         sequence), full batch or one mask per step (masks: (n_steps, n_mask) local sample ids).  Single GPU or the fused
         peer all-reduce only (the torch.distributed all-reduce sits between the gradient and the update of every step).
         Returns the list of per-step result dicts of `step` (without singular values)."""
+        self._advanced = None
         if self.world > 1 and not self.peer:
             raise RuntimeError('sweep() needs the fused peer all-reduce with several ranks; use step()/epoch()')
         b = np.ascontiguousarray(np.asarray(bonds, dtype=np.int32))
