@@ -271,3 +271,45 @@ def test_step_by_step_uploads_only_foreign_tensors(T):
     c, bytes_c = run(True, False)
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and all(np.array_equal(x, y) for x, y in zip(a, c))
     assert bytes_a < bytes_c < bytes_b
+
+
+def test_sequential_update_sees_a_tensor_the_user_changed(T):
+    """learning_step_cached enqueues the environment advance of its own result right away; a user who changes the
+    tensor before calling sequential_update (TNutils.py:504-526) must get the cache of the CHANGED tensor."""
+    np.random.seed(41)
+    imgs = (np.random.default_rng(42).random((40, 10)) < 0.4).astype(np.int64)
+    data = np.array([T.tens_picture(img) for img in imgs])
+    mps = T.initialize_mps(10, 4)
+    cache = T.left_right_cache(mps, data, max_bond=8)
+    for k in range(0, 4):
+        tn = T.learning_step_cached(mps, k, data, 0.05, cache, True, max_bond=8, renorm='l2')
+        T._write_back(mps, k, tn)
+        if k == 2:
+            mps.tensors[k].modify(data=mps.tensors[k].data * 0.5)
+        T.sequential_update(mps, data, cache, k, True)
+        nll_cached = T.computeNLL_cached(mps, data, cache, k + 1)
+        fresh = T.left_right_cache(mps.copy(), data, max_bond=8)
+        nll_fresh = T.computeNLL_cached(mps, data, fresh, k + 1)
+        assert abs(nll_cached - nll_fresh) < 1e-10, (k, nll_cached, nll_fresh)
+
+
+def test_staged_download_equals_the_converted_one(T):
+    """bm_step(advance & 2) leaves the two new tensors in the reference layout so that get_site is a plain copy
+    overlapping the environment advance: same bytes as the conversion path."""
+    from mps_born_machines_b200 import BornEngine, mpslib
+    L, D, N = 12, 8, 64
+    imgs = mpslib.synthetic_images(N, L, seed=5, p_on=0.4)
+    mps = mpslib.random_mps(L, D, rng=np.random.default_rng(6), centre=3)
+    outs = []
+    for staged in (True, False):
+        eng = BornEngine(L, D)
+        eng.set_data(imgs); eng.set_mps(mps); eng.env_build(3)
+        res = []
+        for k in range(3, 7):
+            eng.step(k, 0.05, True, 'l2', max_bond=D, stage_sites=staged)
+            res.append((eng.get_site(k), eng.get_site(k + 1)))
+        res.append(tuple(eng.get_mps()))
+        outs.append(res)
+        eng.close()
+    for ra, rb in zip(*outs):
+        assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
