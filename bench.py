@@ -117,7 +117,8 @@ class ClockSampler:
     Q = 'timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, period_ms=10):
+        self.period_ms = int(period_ms)
         self.path = tempfile.mktemp(suffix='.csv')
         self.proc = None
         self.gpu = gpu_index
@@ -127,7 +128,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.gpu), '-lms', '10'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          '-i', str(self.gpu), '-lms', str(self.period_ms)], stdout=self.f, stderr=subprocess.DEVNULL)
             t_end = time.time() + wait_s
             while time.time() < t_end and os.path.getsize(self.path) == 0:     # first sample printed: sampler is live
                 time.sleep(0.01)
@@ -301,7 +302,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
     flush = None
-    if shard.shape[0] * D * 8 * 2 < 2 * 126e6:
+    if shard.shape[0] * D * 8 * 2 < 2 * 126e6 or getattr(args, 'per_step', False):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f'cuda:{local}')
 
     def barrier():
@@ -318,7 +319,7 @@ def measure_steps(args, workload, rank, world, local, full=True):
     kw = dict(renorm='l2', max_bond=D, cutoff=1e-10)
     lr = LR.get(workload, 1e-3)
     k = start
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, getattr(args, 'clock_ms', 10))
     if rank == 0 and full:
         clocks.start()                    # live before the warm-up: the timed region is shorter than its start-up
     for _ in range(warm):
@@ -700,6 +701,8 @@ def main():
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32', 'tf32_reg'],
                     help="fp64 (default, 1e-6 parity) or tf32 (gradient accumulation on tcgen05/TMEM, 1e-3 parity)")
     ap.add_argument('--sampler-bond', type=int, default=500)
+    ap.add_argument('--per-step', action='store_true', help='time every step as its own call with an L2 flush in between, also at N=1')
+    ap.add_argument('--clock-ms', type=int, default=10, help='nvidia-smi sampling period of the clocks line')
     args = ap.parse_args()
     if args.workload == 'c4':
         run_sampler(args)

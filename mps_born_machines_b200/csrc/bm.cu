@@ -106,6 +106,7 @@ struct bm_ctx {
   int sample_fused = 0;         // BM_SAMPLE_FUSED=1: always the single-launch sampler step (both branches per 64-row tile)
   int wy_pending = 0;           // k_wy_T of the current reflectors is in flight on the side stream
   int eig_debug = 0;         // BM_EIG_DEBUG=1: per-level stage times of the on-chip split on stderr
+  int step_sync = 0;         // BM_STEP_SYNC=1: bm_step returns only after the environment advance has finished
   std::vector<std::pair<const char*, cudaEvent_t>> dbg_ticks;
   int eig_prof = 0; cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; float eig_ms[5] = {0, 0, 0, 0, 0};
   int* info = nullptr; int* iscal = nullptr;
@@ -331,6 +332,7 @@ int eig_setup(bm_ctx* c) {
   CU(cudaMallocHost((void**)&c->h_dev, DEV_SLOTS * sizeof(double)));
   c->eig_ok = 1;
   if (const char* dbg = std::getenv("BM_EIG_DEBUG")) c->eig_debug = std::atoi(dbg);
+  if (const char* ss = std::getenv("BM_STEP_SYNC")) c->step_sync = std::atoi(ss);
   if (const char* v = std::getenv("BM_SAMPLE_FUSED")) c->sample_fused = std::atoi(v);
   if (const char* v = std::getenv("BM_SYTRD_TAIL")) c->sytrd_tail = std::atoi(v);
   if (const char* v = std::getenv("BM_GRAM_TAU")) GRAM_TAU = std::atof(v);
@@ -1554,7 +1556,7 @@ static int update_tail(bm_ctx* c, int k, const double* S_dev, const double* tail
     r = do_advance();
     if (r != BM_OK) return r;
     dbg_tick(c, "advance]");
-    if (c->eig_debug) WAIT();       // the debug ticks are read below
+    if (c->eig_debug || c->step_sync) WAIT();       // the debug ticks are read below
     else {
       r = poll_sync(c);
       if (r != BM_OK) return r;
