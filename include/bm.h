@@ -77,7 +77,12 @@ int bm_set_precision(bm_ctx* ctx, int grad_tf32);
  * left of the centre and the right environment for bonds right of it). */
 int bm_set_data(bm_ctx* ctx, const uint8_t* pixels_host, int n_samples);
 
-/* a2 (data movement part of initialize_mps, TNutils.py:386-424, and of the write-back :1612-1617). */
+/* a2 (data movement part of initialize_mps, TNutils.py:386-424, and of the write-back :1612-1617).
+ * lrp_host: (Dl, Dr, d) doubles, C order (the reference's site layout; d = 2: (i_{k-1}, i_k, v_k)).  Both calls are
+ * synchronous for the caller (the host buffer may be pageable and is free on return) but move the data on the
+ * context's SIDE stream, so they overlap whatever the main stream is still running -- in particular the environment
+ * advance that bm_step leaves in flight.  bm_set_site orders only its layout conversion on the main stream;
+ * bm_get_site waits for the last launch that wrote a site tensor, not for kernels that merely read them. */
 int bm_set_site(bm_ctx* ctx, int k, const double* lrp_host, int Dl, int Dr);
 int bm_get_site(bm_ctx* ctx, int k, double* lrp_host, int* Dl, int* Dr);
 int bm_site_dims(bm_ctx* ctx, int k, int* Dl, int* Dr);
