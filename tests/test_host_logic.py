@@ -193,3 +193,62 @@ def test_enum_values_match_header():
                          'gram_syevd': vals['BM_SVD_GRAM_SYEVD']}
     assert _capi.RENORM == {'max': vals['BM_RENORM_MAX'], 'l2': vals['BM_RENORM_L2']}
     assert _capi.RULE == {'batched': vals['BM_RULE_BATCHED'], 'single': vals['BM_RULE_SINGLE']}
+
+
+class _StubEngine:
+    """Records the engine calls of the facade's step-by-step path (no GPU): the bookkeeping that decides whether
+    `sequential_update` still has work to do after `learning_step_cached` enqueued the advance itself."""
+    def __init__(self):
+        self.calls = []
+        self._handed_out = {}
+        self._advanced = None
+        self._h2d_bytes = 0
+
+    def set_site(self, k, t):
+        self._advanced = None
+        self.calls.append(('set_site', k))
+
+    def env_build(self, k):
+        self.calls.append(('env_build', k))
+
+    def env_advance(self, k, going_right):
+        self.calls.append(('env_advance', k, bool(going_right)))
+
+
+def test_sequential_update_skips_only_the_advance_its_step_already_enqueued():
+    """TNutils.py:1603-1620: learning_step_cached -> write-back -> sequential_update.  The facade's step enqueues the
+    environment advance right behind its split; sequential_update may skip it ONLY when both tensors are still the
+    arrays that step handed out and the direction is the same."""
+    from types import SimpleNamespace
+    from mps_born_machines_b200 import TNutils as T
+    a, b = np.ones((2, 3, 2)), np.ones((3, 2, 2))
+    a.flags.writeable = False; b.flags.writeable = False
+
+    def fresh():
+        eng = _StubEngine()
+        eng._handed_out = {4: a, 5: b}
+        eng._advanced = (4, True)
+        mps = SimpleNamespace(tensors={4: SimpleNamespace(data=a.transpose(0, 1, 2)), 5: SimpleNamespace(data=b)})
+        return eng, mps, SimpleNamespace(engine=eng)
+
+    eng, mps, cache = fresh()                                   # untouched result, same direction: nothing to do
+    T.sequential_update(mps, None, cache, 4, True)
+    assert eng.calls == [] and eng._advanced is None
+    T.sequential_update(mps, None, cache, 4, True)              # a second call is a real cache refresh again
+    assert eng.calls == [('env_build', 4), ('env_advance', 4, True)]
+
+    eng, mps, cache = fresh()                                   # other direction: the enqueued advance does not cover it
+    T.sequential_update(mps, None, cache, 4, False)
+    assert eng.calls == [('env_build', 4), ('env_advance', 4, False)]
+
+    eng, mps, cache = fresh()                                   # the user replaced a tensor: upload + full refresh
+    mps.tensors[4].data = a * 0.5
+    T.sequential_update(mps, None, cache, 4, True)
+    assert eng.calls == [('set_site', 4), ('env_build', 4), ('env_advance', 4, True)]
+    assert 4 not in eng._handed_out and eng._h2d_bytes == a.nbytes
+
+    eng, mps, cache = fresh()                                   # another bond: not the step that was advanced
+    eng._handed_out = {7: a, 8: b}
+    mps.tensors = {7: SimpleNamespace(data=a), 8: SimpleNamespace(data=b)}
+    T.sequential_update(mps, None, cache, 7, True)
+    assert eng.calls == [('env_build', 7), ('env_advance', 7, True)]
