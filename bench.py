@@ -374,6 +374,19 @@ def measure_steps(args, workload, rank, world, local, full=True):
         return rec
 
     trace('timed region done')
+    # ---- replicas: every rank carries the whole MPS and repeats the split on the all-reduced gradient; after the timed
+    #      steps the site tensors must be IDENTICAL on all ranks (checksum spread 0.0).  Untimed.
+    try:
+        cs, nsite = 0.0, 0
+        for j in range(start, min(k + 2, L)):
+            t = eng.get_site(j).ravel()
+            cs += float(np.dot(t, np.cos(np.arange(t.size, dtype=np.float64))))
+            nsite += 1
+        hi, lo = max_over_ranks(cs), -max_over_ranks(-cs)
+        rec['multi_gpu_parity'] = {'replica_checksum_spread': hi - lo, 'replicas_identical': bool(hi == lo), 'sites_compared': nsite,
+                                   'ranks': world, 'teacher_forced_vs_single_gpu': 'tests/test_gpu_multirank.py (profiles/r02_multirank_parity_2gpu.jsonl)'}
+    except Exception as exc:                  # never lose the bench line over the side check
+        rec['multi_gpu_parity'] = {'error': str(exc)[:200]}
     # ---- e2e (a): the reference's own call sequence through the facade with HOST tensors, every step:
     #      learning_step_cached -> write the two tensors back into the host MPS -> sequential_update
     #      (TNutils.py:1603-1620).  Uploads the site tensor the engine has not produced itself and downloads 2 per step (pageable numpy memory, as a
@@ -547,7 +560,7 @@ def run_ours(args):
             'gram_levels': rec['gram_levels'], 'wall_s_timed': rec['wall_s_timed'], 'setup_s': rec['setup_s'],
             'sweep_s_extrapolated': rec['ms_per_step'] * 1e-3 * 2 * (L - 1),
         }
-        for key in ('full_sweep', 'sampler'):
+        for key in ('full_sweep', 'sampler', 'multi_gpu_parity'):
             if key in rec:
                 line[key] = rec[key]
         if cpu:
